@@ -1,0 +1,61 @@
+"""Build libfocr_b200.so in-tree with nvcc for sm_100a (and nothing else).
+
+    python font-ocr_b200/build.py [--force]
+
+The library is the product: hand-written CUDA kernels + the C ABI of include/focr_b200.h.
+It is built in-tree (font-ocr_b200/libfocr_b200.so, git-ignored) so that it travels to the GPU
+box with the gpurun snapshot.  cudart is linked statically and libcuda is only reached through
+cudaGetDriverEntryPoint, so the .so also loads on a machine without a driver (the CPU test box),
+where every compute entry then returns FOCR_ERR_CUDA.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libfocr_b200.so")
+STAMP = OUT + ".stamp"
+SOURCES = ["api.cu", "stats.cu", "scan_simt.cu", "scan_tc.cu", "finalize.cu", "focr_decode.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--fmad=false",              # no implicit contraction: the only fused ops are the explicit __fma_rn
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off",
+    "-shared", "-cudart", "static",
+]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    files = sorted(os.listdir(CSRC)) + ["../../include/focr_b200.h", "../build.py"]
+    for f in files:
+        p = os.path.join(CSRC, f)
+        if os.path.isfile(p):
+            h.update(f.encode())
+            h.update(open(p, "rb").read())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    dg = _digest()
+    if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read() == dg:
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libfocr_b200.so")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    open(STAMP, "w").write(dg)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,807 @@
+// api.cu -- the C ABI of libfocr_b200.so (include/focr_b200.h): contexts, template banks, the
+// batched scan pipeline (H2D -> stage -> stats -> scan -> finalize -> D2H) and the compat shim that
+// exports the reference's own `ncc_8_u8` / `ncc_16_u8` symbols (ncc.cpp:48-63, 253-268).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "scan_tc.cuh"
+#include "focr_decode.cuh"
+
+using namespace focr;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(FOCR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+extern "C" const char *focr_last_error(void) { return g_err.c_str(); }
+extern "C" const char *focr_version(void) { return "focr_b200 0.1 (sm_100a)"; }
+extern "C" void focr_get_limits(focr_limits *out)
+{
+    if (!out) return;
+    out->max_template_w = MAX_TPL_W;
+    out->max_template_h = MAX_TPL_H;
+    out->max_page_w = 15360;  // finalize_sel_cap: n_out + r_w keys must fit the shared-memory sort
+    out->max_page_h = 65535;
+    out->max_n_out = 4096;
+}
+
+// ------------------------------------------------------------------------------------------ buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaError_t e = cudaFree(p);
+            if (e != cudaSuccess) return e;
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return (T *)p; }
+};
+
+struct Slot {  // everything one in-flight chunk of pages needs
+    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, sel, ycut, selcount, flags, out, counts, acc;
+    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
+    uint32_t hits_per_page = 0;
+};
+
+struct focr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    int kernel = FOCR_KERNEL_AUTO;
+    uint64_t launches = 0;
+    Slot slot[2];
+    uint32_t hits_per_page = 2u << 20;
+    int sm_count = 148;
+    TcWorkspace tc;
+    // per-stage profiling (focr_ctx_profile)
+    bool profile = false;
+    struct Span { cudaEvent_t a, b; int stage; int launches; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t get_event()
+    {
+        if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+
+struct StageTimer {  // RAII: events around one stage when profiling is on
+    focr_ctx *c; int stage; int launches; cudaEvent_t a = nullptr;
+    StageTimer(focr_ctx *c_, int stage_, int launches_ = 1) : c(c_), stage(stage_), launches(launches_)
+    {
+        if (c->profile) { a = c->get_event(); cudaEventRecord(a, c->stream); }
+    }
+    ~StageTimer()
+    {
+        if (a) { cudaEvent_t b = c->get_event(); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, stage, launches}); }
+    }
+};
+
+struct ClassHost {
+    uint32_t n_w, n_h, np;
+    std::vector<uint32_t> index;
+    DevBuf rows, index_dev;
+    TcClass tc;  // tcgen05 operand layout of this class (scan_tc.cu)
+};
+
+struct focr_bank {
+    focr_ctx *ctx = nullptr;
+    uint32_t T = 0;
+    std::vector<ClassHost> classes;
+    std::vector<TplInfo> info;
+    DevBuf info_dev;
+};
+
+// ------------------------------------------------------------------------------------------ context
+extern "C" int focr_ctx_create(int device, focr_ctx **out)
+{
+    if (!out) return fail(FOCR_ERR_ARG, "focr_ctx_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FOCR_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                       " (libfocr_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(FOCR_ERR_ARG, "focr_ctx_create: bad device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FOCR_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                              "; libfocr_b200 is built for sm_100a only");
+    focr_ctx *c = new focr_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (auto &s : c->slot) {
+        CU(cudaMallocHost((void **)&s.flags_host, 64));
+        memset(s.flags_host, 0, 64);
+        CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
+    }
+    *out = c;
+    return FOCR_OK;
+}
+
+extern "C" void focr_ctx_destroy(focr_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slot) {
+        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.sel, &s.ycut,
+                          &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
+            b->release();
+        if (s.flags_host) cudaFreeHost(s.flags_host);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_compute) cudaEventDestroy(s.ev_compute);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    }
+    tc_workspace_release(c->tc);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->h2d);
+    cudaStreamDestroy(c->d2h);
+    delete c;
+}
+
+extern "C" int focr_ctx_set_kernel(focr_ctx *c, int kernel)
+{
+    if (!c || kernel < FOCR_KERNEL_AUTO || kernel > FOCR_KERNEL_TCGEN05)
+        return fail(FOCR_ERR_ARG, "focr_ctx_set_kernel: bad argument");
+    c->kernel = kernel;
+    return FOCR_OK;
+}
+extern "C" void *focr_ctx_stream(focr_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int focr_ctx_sync(focr_ctx *c)
+{
+    if (!c) return fail(FOCR_ERR_ARG, "focr_ctx_sync: NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->h2d));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->d2h));
+    return FOCR_OK;
+}
+extern "C" uint64_t focr_ctx_launch_count(const focr_ctx *c) { return c ? c->launches : 0; }
+extern "C" int focr_ctx_profile(focr_ctx *c, int enable)
+{
+    if (!c) return fail(FOCR_ERR_ARG, "focr_ctx_profile: NULL");
+    c->profile = enable != 0;
+    return FOCR_OK;
+}
+extern "C" int focr_ctx_profile_read(focr_ctx *c, double *ms_out, uint64_t *launches_out)
+{
+    if (!c || !ms_out || !launches_out) return fail(FOCR_ERR_ARG, "focr_ctx_profile_read: NULL");
+    int rc = focr_ctx_sync(c);
+    if (rc) return rc;
+    for (int i = 0; i < FOCR_N_STAGES; i++) { ms_out[i] = 0; launches_out[i] = 0; }
+    for (auto &sp : c->spans) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_out[sp.stage] += ms;
+        launches_out[sp.stage] += sp.launches;
+        c->event_pool.push_back(sp.a);
+        c->event_pool.push_back(sp.b);
+    }
+    c->spans.clear();
+    return FOCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ bank
+static void tpl_info(const uint8_t *px, uint32_t n_w, uint32_t n_h, TplInfo &ti)
+{
+    // ncc.cpp:73-86 (the zero padding adds nothing to either sum)
+    uint32_t s_n = 0, s2_n = 0;
+    for (uint32_t i = 0; i < n_w * n_h; i++) {
+        s_n += px[i];
+        s2_n += (uint32_t)px[i] * (uint32_t)px[i];
+    }
+    const size_t n = (size_t)n_w * n_h;
+    volatile double q = (double)((uint64_t)s_n * (uint64_t)s_n) / (double)n;  // volatile: no contraction
+    const double norm2_n = (double)s2_n - q;
+    ti.rnorm_n = 1. / std::sqrt(norm2_n);
+    ti.n_recip = 1. / (double)n;
+    ti.s_n = (double)s_n;
+    ti.n_w = n_w;
+    ti.n_h = n_h;
+}
+
+extern "C" int focr_bank_create(focr_ctx *c, const uint8_t *pixels, const uint64_t *offsets, const uint16_t *n_w,
+                                const uint16_t *n_h, uint32_t T, focr_bank **out)
+{
+    if (!c || !pixels || !offsets || !n_w || !n_h || !out || T == 0)
+        return fail(FOCR_ERR_ARG, "focr_bank_create: NULL argument or empty bank");
+    CU(cudaSetDevice(c->device));
+    focr_bank *b = new focr_bank();
+    b->ctx = c;
+    b->T = T;
+    b->info.resize(T);
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> cls_of;
+    for (uint32_t t = 0; t < T; t++) {
+        const uint32_t w = n_w[t], h = n_h[t];
+        if (w == 0 || h == 0 || w > MAX_TPL_W || h > MAX_TPL_H) {
+            delete b;
+            return fail(FOCR_ERR_UNSUPPORTED, "focr_bank_create: template " + std::to_string(t) + " is " +
+                                                  std::to_string(w) + "x" + std::to_string(h) + "; supported 1..32 x 1..64");
+        }
+        auto key = std::make_pair(w, h);
+        auto it = cls_of.find(key);
+        if (it == cls_of.end()) {
+            it = cls_of.emplace(key, (uint32_t)b->classes.size()).first;
+            ClassHost ch;
+            ch.n_w = w;
+            ch.n_h = h;
+            ch.np = w <= 16 ? 16 : 32;
+            b->classes.push_back(std::move(ch));
+        }
+        tpl_info(pixels + offsets[t], w, h, b->info[t]);
+        b->info[t].cls = it->second;
+        b->info[t].data_off = (uint32_t)b->classes[it->second].index.size() * h * b->classes[it->second].np;
+        b->classes[it->second].index.push_back(t);
+    }
+    for (auto &ch : b->classes) {
+        // copy_needle_n_u8 (ncc.rs:925-935): rows zero-padded to np bytes
+        std::vector<uint8_t> rows((size_t)ch.index.size() * ch.n_h * ch.np, 0);
+        for (size_t i = 0; i < ch.index.size(); i++) {
+            const uint8_t *src = pixels + offsets[ch.index[i]];
+            for (uint32_t y = 0; y < ch.n_h; y++)
+                memcpy(&rows[(i * ch.n_h + y) * ch.np], src + (size_t)y * ch.n_w, ch.n_w);
+        }
+        CU(ch.rows.ensure(rows.size()));
+        CU(cudaMemcpy(ch.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+        CU(ch.index_dev.ensure(ch.index.size() * 4));
+        CU(cudaMemcpy(ch.index_dev.p, ch.index.data(), ch.index.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<TplInfo> cls_info;
+        for (uint32_t t : ch.index) cls_info.push_back(b->info[t]);
+        int rc = tc_class_build(ch.tc, rows.data(), ch.n_w, ch.n_h, ch.np, (uint32_t)ch.index.size(), ch.index.data(),
+                                cls_info.data());
+        if (rc != 0) {
+            delete b;
+            return fail(FOCR_ERR_CUDA, "focr_bank_create: tcgen05 operand upload failed");
+        }
+    }
+    CU(b->info_dev.ensure(T * sizeof(TplInfo)));
+    CU(cudaMemcpy(b->info_dev.p, b->info.data(), T * sizeof(TplInfo), cudaMemcpyHostToDevice));
+    *out = b;
+    return FOCR_OK;
+}
+
+extern "C" void focr_bank_destroy(focr_bank *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &ch : b->classes) {
+        ch.rows.release();
+        ch.index_dev.release();
+        tc_class_release(ch.tc);
+    }
+    b->info_dev.release();
+    delete b;
+}
+extern "C" uint32_t focr_bank_size(const focr_bank *b) { return b ? b->T : 0; }
+
+// ------------------------------------------------------------------------------------------ scan pipeline
+struct Geometry {
+    uint32_t r_w, r_h, n_out;
+    int pitch;       // inverted page pitch (bytes, multiple of 128)
+    int spitch;      // stats plane pitch (elements, multiple of 32)
+    size_t inv_page_stride, plane_page_stride;
+    uint32_t sel_cap;
+};
+
+static int make_geometry(uint32_t r_w, uint32_t r_h, uint32_t n_out, Geometry &g)
+{
+    if (r_w == 0 || r_h == 0 || r_w > 65535 || r_h > 65535) return fail(FOCR_ERR_ARG, "page dimensions must fit u16");
+    if (n_out == 0 || n_out > 4096) return fail(FOCR_ERR_ARG, "n_out must be in 1..4096");
+    g.r_w = r_w;
+    g.r_h = r_h;
+    g.n_out = n_out;
+    g.pitch = (int)((r_w + 32 + 127) / 128 * 128);  // >= r_w + 32: any 32-byte window row may over-read
+    g.spitch = (int)((r_w + 31) / 32 * 32);
+    g.inv_page_stride = (size_t)g.pitch * (r_h + PAGE_PAD_ROWS);
+    g.plane_page_stride = (size_t)g.spitch * r_h;
+    const size_t sc = finalize_sel_cap(r_w, n_out);
+    if (sc == 0) return fail(FOCR_ERR_UNSUPPORTED, "page wider than 15360 px is not supported yet");
+    g.sel_cap = (uint32_t)sc;
+    return FOCR_OK;
+}
+
+static bool use_tc(const focr_ctx *c, const ClassHost &ch)
+{
+    if (c->kernel == FOCR_KERNEL_SIMT) return false;
+    return tc_class_supported(ch.tc);
+}
+
+// enqueue the whole device pipeline for nB pages that sit (gray or inverted) in device memory
+static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometry &g, const uint8_t *pages_dev,
+                         size_t page_stride, size_t in_pitch, uint32_t nB, float threshold, int invert,
+                         focr_match *out_dev, uint32_t *counts_dev)
+{
+    cudaStream_t st = c->stream;
+    const uint32_t T = b->T;
+    bool any_simt = false;
+    for (auto &ch : b->classes) {
+        if (c->kernel == FOCR_KERNEL_TCGEN05 && !tc_class_supported(ch.tc))
+            return fail(FOCR_ERR_UNSUPPORTED, "tcgen05 kernel does not support box " + std::to_string(ch.n_w) + "x" +
+                                                  std::to_string(ch.n_h));
+        any_simt |= !use_tc(c, ch);
+    }
+    if (s.hits_per_page < c->hits_per_page) s.hits_per_page = c->hits_per_page;
+    const size_t hit_cap = (size_t)s.hits_per_page * nB;
+    const size_t PT = (size_t)nB * T;
+    CU(s.inv.ensure(g.inv_page_stride * nB));
+    CU(s.sp.ensure(g.plane_page_stride * nB * 4));
+    CU(s.s2p.ensure(g.plane_page_stride * nB * 4));
+    CU(s.pf.ensure(g.plane_page_stride * nB * 4));
+    if (any_simt) CU(s.rn.ensure(g.plane_page_stride * nB * 8));
+    CU(s.rowcount.ensure(PT * g.r_h * 4));
+    CU(s.hits.ensure(hit_cap * sizeof(Hit)));
+    CU(s.sel.ensure(PT * g.sel_cap * 8));
+    CU(s.ycut.ensure(PT * 4));
+    CU(s.selcount.ensure(PT * 4));
+    CU(s.flags.ensure(64));
+
+    {
+        StageTimer tm(c, FOCR_STAGE_INVERT);
+        CU(launch_stage_invert(pages_dev, page_stride, in_pitch, s.inv.as<uint8_t>(), g.inv_page_stride, g.pitch,
+                               g.r_w, g.r_h, nB, invert, st));
+    }
+    c->launches++;
+    CU(cudaMemsetAsync(s.rowcount.p, 0, PT * g.r_h * 4, st));
+    CU(cudaMemsetAsync(s.selcount.p, 0, PT * 4, st));
+    CU(cudaMemsetAsync(s.flags.p, 0, 64, st));
+
+    HitSink sink;
+    sink.hits = s.hits.as<Hit>();
+    sink.hit_cap = (uint32_t)std::min<size_t>(hit_cap, 0xFFFFFFFFu);
+    sink.hit_count = s.flags.as<unsigned int>();
+    sink.rowcount = s.rowcount.as<unsigned int>();
+    sink.T = T;
+    sink.r_h = g.r_h;
+
+    for (auto &ch : b->classes) {
+        if (ch.n_w > g.r_w || ch.n_h > g.r_h) continue;  // no window fits: no hits for these templates
+        const bool tc = use_tc(c, ch);
+        StatsArgs sa;
+        sa.inv = s.inv.as<uint8_t>();
+        sa.inv_page_stride = g.inv_page_stride;
+        sa.pitch = g.pitch;
+        sa.r_w = g.r_w;
+        sa.r_h = g.r_h;
+        sa.n_w = ch.n_w;
+        sa.n_h = ch.n_h;
+        sa.inv_n_f = 1.0f / (float)(ch.n_w * ch.n_h);
+        sa.sp = s.sp.as<uint32_t>();
+        sa.s2p = s.s2p.as<uint32_t>();
+        sa.pf = s.pf.as<float>();
+        sa.rn = tc ? nullptr : s.rn.as<double>();
+        sa.spitch = g.spitch;
+        sa.plane_page_stride = g.plane_page_stride;
+        {
+            StageTimer tm(c, FOCR_STAGE_STATS);
+            CU(launch_window_stats(sa, nB, st));
+        }
+        c->launches++;
+
+        ScanArgs a;
+        a.inv = sa.inv;
+        a.inv_page_stride = g.inv_page_stride;
+        a.pitch = g.pitch;
+        a.r_w = g.r_w;
+        a.r_h = g.r_h;
+        a.cls.n_w = ch.n_w;
+        a.cls.n_h = ch.n_h;
+        a.cls.np = ch.np;
+        a.cls.n_tpl = (uint32_t)ch.index.size();
+        a.cls.tpl_index = ch.index_dev.as<uint32_t>();
+        a.cls.rows = ch.rows.as<uint8_t>();
+        a.tpl = b->info_dev.as<TplInfo>();
+        a.sp = sa.sp;
+        a.s2p = sa.s2p;
+        a.pf = sa.pf;
+        a.rn = sa.rn;
+        a.spitch = g.spitch;
+        a.plane_page_stride = g.plane_page_stride;
+        a.thr_d = (double)threshold;  // ncc.cpp:83
+        a.thr_f = threshold;
+        a.sink = sink;
+        a.acc_out = nullptr;
+        int nl = 0;
+        {
+            StageTimer tm(c, FOCR_STAGE_SCAN);
+            if (tc)
+                CU(launch_scan_tc(c->tc, ch.tc, a, nB, c->sm_count, st, &nl));
+            else
+                CU(launch_scan_simt(a, nB, st, &nl));
+            tm.launches = nl;
+        }
+        c->launches += nl;
+    }
+
+    FinalizeArgs f;
+    f.hits = s.hits.as<Hit>();
+    f.hit_count = s.flags.as<unsigned int>();
+    f.hit_cap = sink.hit_cap;
+    f.rowcount = s.rowcount.as<unsigned int>();
+    f.y_cut = s.ycut.as<uint32_t>();
+    f.sel_count = s.selcount.as<unsigned int>();
+    f.sel = s.sel.as<unsigned long long>();
+    f.sel_cap = g.sel_cap;
+    f.overflow = s.flags.as<unsigned int>() + 1;
+    f.T = T;
+    f.r_h = g.r_h;
+    f.n_pages = nB;
+    f.n_out = g.n_out;
+    f.out = out_dev;
+    f.counts = counts_dev;
+    int nl = 0;
+    {
+        StageTimer tm(c, FOCR_STAGE_FINALIZE, 3);
+        CU(launch_finalize(f, st, &nl));
+    }
+    c->launches += nl;
+    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 8, cudaMemcpyDeviceToHost, st));
+    return FOCR_OK;
+}
+
+// after the stream has been synchronised: did the chunk's hit list overflow?
+static bool chunk_overflowed(focr_ctx *c, Slot &s, uint32_t nB)
+{
+    const size_t cap = (size_t)s.hits_per_page * nB;
+    if (s.flags_host[0] > cap) {
+        const size_t need = ((size_t)s.flags_host[0] + nB - 1) / nB;
+        c->hits_per_page = (uint32_t)std::min<size_t>(need + need / 4 + 1024, 0x7FFFFFFFu);
+        return true;
+    }
+    return false;
+}
+
+static uint32_t pick_chunk(const focr_bank *b, const Geometry &g, uint32_t n_pages, uint32_t hits_per_page)
+{
+    const size_t per_page = g.inv_page_stride + (size_t)g.r_w * g.r_h + g.plane_page_stride * 20 +
+                            (size_t)b->T * g.r_h * 4 + (size_t)hits_per_page * sizeof(Hit) +
+                            (size_t)b->T * g.sel_cap * 8 + (size_t)b->T * g.n_out * 8;
+    size_t nb = (size_t)(6ull << 30) / std::max<size_t>(per_page, 1);
+    nb = std::max<size_t>(1, std::min<size_t>(nb, 16));
+    return (uint32_t)std::min<size_t>(nb, n_pages);
+}
+
+extern "C" int focr_ncc_scan_device(focr_ctx *c, const focr_bank *b, const uint8_t *pages_dev, size_t page_stride,
+                                    size_t pitch, uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold,
+                                    uint32_t n_out, focr_match *out_dev, uint32_t *counts_dev)
+{
+    if (!c || !b || !pages_dev || !out_dev || !counts_dev || n_pages == 0)
+        return fail(FOCR_ERR_ARG, "focr_ncc_scan_device: NULL argument or no pages");
+    if (b->ctx != c) return fail(FOCR_ERR_ARG, "bank belongs to another context");
+    CU(cudaSetDevice(c->device));
+    Geometry g;
+    int rc = make_geometry(r_w, r_h, n_out, g);
+    if (rc) return rc;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const uint32_t B = pick_chunk(b, g, n_pages, c->hits_per_page);
+        bool redo = false;
+        for (uint32_t p0 = 0; p0 < n_pages && !redo; p0 += B) {
+            const uint32_t nB = std::min(B, n_pages - p0);
+            Slot &s = c->slot[0];
+            rc = enqueue_chunk(c, b, s, g, pages_dev + (size_t)p0 * page_stride, page_stride, pitch, nB, threshold, 1,
+                               out_dev + (size_t)p0 * b->T * n_out, counts_dev + (size_t)p0 * b->T);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(c->stream));
+            if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+            redo = chunk_overflowed(c, s, nB);
+        }
+        if (!redo) return FOCR_OK;
+    }
+    return fail(FOCR_ERR_NOMEM, "hit list kept overflowing");
+}
+
+static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_host, size_t page_stride,
+                          uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out, int invert,
+                          focr_match *out_host, uint32_t *counts_host)
+{
+    CU(cudaSetDevice(c->device));
+    Geometry g;
+    int rc = make_geometry(r_w, r_h, n_out, g);
+    if (rc) return rc;
+    const size_t page_bytes = (size_t)r_w * r_h;
+    const uint32_t T = b->T;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        const uint32_t B = pick_chunk(b, g, n_pages, c->hits_per_page);
+        std::vector<uint32_t> chunk_slot;
+        bool redo = false;
+        uint32_t ci = 0;
+        // software pipeline over chunks: H2D of chunk i+1 overlaps the kernels of chunk i,
+        // D2H of chunk i overlaps the kernels of chunk i+1
+        for (uint32_t p0 = 0; p0 < n_pages; p0 += B, ci++) {
+            const uint32_t nB = std::min(B, n_pages - p0);
+            Slot &s = c->slot[ci & 1];
+            if (ci >= 2) {  // the slot's previous chunk must be fully drained before its buffers are reused
+                CU(cudaEventSynchronize(s.ev_d2h));
+                if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+                if (chunk_overflowed(c, s, std::min(B, n_pages - (p0 - 2 * B)))) {
+                    redo = true;
+                    break;
+                }
+            }
+            CU(s.gray.ensure(page_bytes * nB));
+            CU(s.out.ensure((size_t)nB * T * n_out * sizeof(focr_match)));
+            CU(s.counts.ensure((size_t)nB * T * 4));
+            if (page_stride == page_bytes) {
+                CU(cudaMemcpyAsync(s.gray.p, pages_host + (size_t)p0 * page_stride, page_bytes * nB,
+                                   cudaMemcpyHostToDevice, c->h2d));
+            } else {
+                CU(cudaMemcpy2DAsync(s.gray.p, page_bytes, pages_host + (size_t)p0 * page_stride, page_stride,
+                                     page_bytes, nB, cudaMemcpyHostToDevice, c->h2d));
+            }
+            CU(cudaEventRecord(s.ev_h2d, c->h2d));
+            CU(cudaStreamWaitEvent(c->stream, s.ev_h2d, 0));
+            rc = enqueue_chunk(c, b, s, g, s.gray.as<uint8_t>(), page_bytes, r_w, nB, threshold, invert,
+                               s.out.as<focr_match>(), s.counts.as<uint32_t>());
+            if (rc) return rc;
+            CU(cudaEventRecord(s.ev_compute, c->stream));
+            CU(cudaStreamWaitEvent(c->d2h, s.ev_compute, 0));
+            CU(cudaMemcpyAsync(out_host + (size_t)p0 * T * n_out, s.out.p, (size_t)nB * T * n_out * sizeof(focr_match),
+                               cudaMemcpyDeviceToHost, c->d2h));
+            CU(cudaMemcpyAsync(counts_host + (size_t)p0 * T, s.counts.p, (size_t)nB * T * 4, cudaMemcpyDeviceToHost,
+                               c->d2h));
+            CU(cudaEventRecord(s.ev_d2h, c->d2h));
+        }
+        CU(cudaStreamSynchronize(c->h2d));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->d2h));
+        if (!redo) {
+            // the last (up to) two chunks have not been checked yet
+            const uint32_t n_chunks = ci;
+            for (uint32_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; k++) {
+                Slot &s = c->slot[k & 1];
+                if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+                const uint32_t nB = std::min(B, n_pages - k * B);
+                if (chunk_overflowed(c, s, nB)) redo = true;
+            }
+        }
+        if (!redo) return FOCR_OK;
+    }
+    return fail(FOCR_ERR_NOMEM, "hit list kept overflowing");
+}
+
+extern "C" int focr_ncc_scan(focr_ctx *c, const focr_bank *b, const uint8_t *pages_host, size_t page_stride,
+                             uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
+                             focr_match *out_host, uint32_t *counts_host)
+{
+    if (!c || !b || !pages_host || !out_host || !counts_host || n_pages == 0)
+        return fail(FOCR_ERR_ARG, "focr_ncc_scan: NULL argument or no pages");
+    if (b->ctx != c) return fail(FOCR_ERR_ARG, "bank belongs to another context");
+    if (page_stride < (size_t)r_w * r_h) return fail(FOCR_ERR_ARG, "page_stride smaller than a page");
+    return scan_host_impl(c, b, pages_host, page_stride, r_w, r_h, n_pages, threshold, n_out, 1, out_host, counts_host);
+}
+
+// ------------------------------------------------------------------------------------------ parity probes
+extern "C" int focr_window_stats(focr_ctx *c, const uint8_t *page_gray_host, uint32_t r_w, uint32_t r_h, uint32_t n_w,
+                                 uint32_t n_h, uint32_t *s_p_host, uint64_t *s2_p_host, double *patch_rnorm_host)
+{
+    if (!c || !page_gray_host || !s_p_host || !s2_p_host || !patch_rnorm_host)
+        return fail(FOCR_ERR_ARG, "focr_window_stats: NULL argument");
+    if (n_w == 0 || n_h == 0 || n_w > MAX_TPL_W || n_h > MAX_TPL_H || n_w > r_w || n_h > r_h)
+        return fail(FOCR_ERR_UNSUPPORTED, "focr_window_stats: unsupported box");
+    CU(cudaSetDevice(c->device));
+    Geometry g;
+    int rc = make_geometry(r_w, r_h, 1024, g);
+    if (rc) return rc;
+    Slot &s = c->slot[0];
+    const size_t page_bytes = (size_t)r_w * r_h;
+    CU(s.gray.ensure(page_bytes));
+    CU(s.inv.ensure(g.inv_page_stride));
+    CU(s.sp.ensure(g.plane_page_stride * 4));
+    CU(s.s2p.ensure(g.plane_page_stride * 4));
+    CU(s.pf.ensure(g.plane_page_stride * 4));
+    CU(s.rn.ensure(g.plane_page_stride * 8));
+    CU(cudaMemcpyAsync(s.gray.p, page_gray_host, page_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(launch_stage_invert(s.gray.as<uint8_t>(), page_bytes, r_w, s.inv.as<uint8_t>(), g.inv_page_stride, g.pitch, r_w,
+                           r_h, 1, 1, c->stream));
+    StatsArgs sa;
+    sa.inv = s.inv.as<uint8_t>();
+    sa.inv_page_stride = g.inv_page_stride;
+    sa.pitch = g.pitch;
+    sa.r_w = r_w;
+    sa.r_h = r_h;
+    sa.n_w = n_w;
+    sa.n_h = n_h;
+    sa.inv_n_f = 1.0f / (float)(n_w * n_h);
+    sa.sp = s.sp.as<uint32_t>();
+    sa.s2p = s.s2p.as<uint32_t>();
+    sa.pf = s.pf.as<float>();
+    sa.rn = s.rn.as<double>();
+    sa.spitch = g.spitch;
+    sa.plane_page_stride = g.plane_page_stride;
+    CU(launch_window_stats(sa, 1, c->stream));
+    c->launches += 2;
+    const uint32_t xs = r_w - n_w + 1, ys = r_h - n_h + 1;
+    std::vector<uint32_t> s2((size_t)xs * ys);
+    CU(cudaMemcpy2DAsync(s_p_host, (size_t)r_w * 4, s.sp.p, (size_t)g.spitch * 4, (size_t)xs * 4, ys,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(s2.data(), (size_t)xs * 4, s.s2p.p, (size_t)g.spitch * 4, (size_t)xs * 4, ys,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(patch_rnorm_host, (size_t)r_w * 8, s.rn.p, (size_t)g.spitch * 8, (size_t)xs * 8, ys,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (uint32_t y = 0; y < ys; y++)
+        for (uint32_t x = 0; x < xs; x++) s2_p_host[(size_t)y * r_w + x] = s2[(size_t)y * xs + x];
+    return FOCR_OK;
+}
+
+extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, const uint8_t *page_gray_host,
+                                   uint32_t r_w, uint32_t r_h, uint32_t *acc_host)
+{
+    if (!c || !b || !page_gray_host || !acc_host || t >= b->T)
+        return fail(FOCR_ERR_ARG, "focr_ncc_numerators: bad argument");
+    CU(cudaSetDevice(c->device));
+    Geometry g;
+    int rc = make_geometry(r_w, r_h, 1024, g);
+    if (rc) return rc;
+    const TplInfo &ti = b->info[t];
+    const ClassHost &ch = b->classes[ti.cls];
+    if (ch.n_w > r_w || ch.n_h > r_h) return fail(FOCR_ERR_ARG, "template larger than the page");
+    Slot &s = c->slot[0];
+    const size_t page_bytes = (size_t)r_w * r_h;
+    CU(s.gray.ensure(page_bytes));
+    CU(s.inv.ensure(g.inv_page_stride));
+    CU(s.sp.ensure(g.plane_page_stride * 4));
+    CU(s.s2p.ensure(g.plane_page_stride * 4));
+    CU(s.pf.ensure(g.plane_page_stride * 4));
+    CU(s.rn.ensure(g.plane_page_stride * 8));
+    CU(s.rowcount.ensure((size_t)b->T * r_h * 4));
+    CU(s.hits.ensure(1024 * sizeof(Hit)));
+    CU(s.flags.ensure(64));
+    CU(s.acc.ensure(page_bytes * 4));
+    cudaStream_t st = c->stream;
+    CU(cudaMemcpyAsync(s.gray.p, page_gray_host, page_bytes, cudaMemcpyHostToDevice, st));
+    CU(launch_stage_invert(s.gray.as<uint8_t>(), page_bytes, r_w, s.inv.as<uint8_t>(), g.inv_page_stride, g.pitch, r_w,
+                           r_h, 1, 1, st));
+    CU(cudaMemsetAsync(s.rowcount.p, 0, (size_t)b->T * r_h * 4, st));
+    CU(cudaMemsetAsync(s.flags.p, 0, 64, st));
+    CU(cudaMemsetAsync(s.acc.p, 0, page_bytes * 4, st));
+    StatsArgs sa;
+    sa.inv = s.inv.as<uint8_t>();
+    sa.inv_page_stride = g.inv_page_stride;
+    sa.pitch = g.pitch;
+    sa.r_w = r_w;
+    sa.r_h = r_h;
+    sa.n_w = ch.n_w;
+    sa.n_h = ch.n_h;
+    sa.inv_n_f = 1.0f / (float)(ch.n_w * ch.n_h);
+    sa.sp = s.sp.as<uint32_t>();
+    sa.s2p = s.s2p.as<uint32_t>();
+    sa.pf = s.pf.as<float>();
+    sa.rn = s.rn.as<double>();
+    sa.spitch = g.spitch;
+    sa.plane_page_stride = g.plane_page_stride;
+    CU(launch_window_stats(sa, 1, st));
+    ScanArgs a;
+    a.inv = sa.inv;
+    a.inv_page_stride = g.inv_page_stride;
+    a.pitch = g.pitch;
+    a.r_w = r_w;
+    a.r_h = r_h;
+    a.cls.n_w = ch.n_w;
+    a.cls.n_h = ch.n_h;
+    a.cls.np = ch.np;
+    a.cls.n_tpl = 1;
+    const uint32_t pos = ti.data_off / (ch.n_h * ch.np);
+    a.cls.tpl_index = ch.index_dev.as<uint32_t>() + pos;
+    a.cls.rows = ch.rows.as<uint8_t>() + ti.data_off;
+    a.tpl = b->info_dev.as<TplInfo>();
+    a.sp = sa.sp;
+    a.s2p = sa.s2p;
+    a.pf = sa.pf;
+    a.rn = sa.rn;
+    a.spitch = g.spitch;
+    a.plane_page_stride = g.plane_page_stride;
+    a.thr_d = 2.0;  // nothing is a hit: this probe only wants the numerators
+    a.thr_f = 2.0f;
+    a.sink.hits = s.hits.as<Hit>();
+    a.sink.hit_cap = 1024;
+    a.sink.hit_count = s.flags.as<unsigned int>();
+    a.sink.rowcount = s.rowcount.as<unsigned int>();
+    a.sink.T = b->T;
+    a.sink.r_h = r_h;
+    a.acc_out = s.acc.as<uint32_t>();
+    int nl = 0;
+    CU(launch_scan_simt(a, 1, st, &nl));
+    c->launches += 2 + nl;
+    CU(cudaMemcpyAsync(acc_host, s.acc.p, page_bytes * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FOCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ compat shim
+static std::mutex g_shim_mu;
+static focr_ctx *g_shim_ctx = nullptr;
+
+static size_t shim_scan(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t N, size_t n_w,
+                        size_t n_h, float threshold, focr_match *out, size_t n_out)
+{
+    std::lock_guard<std::mutex> lk(g_shim_mu);
+    auto die = [](const char *what) {
+        fprintf(stderr, "libfocr_b200 shim: %s: %s\n", what, focr_last_error());
+        abort();
+    };
+    if (!g_shim_ctx) {
+        const char *dev = getenv("FOCR_DEVICE");
+        if (focr_ctx_create(dev ? atoi(dev) : 0, &g_shim_ctx) != FOCR_OK) die("focr_ctx_create");
+    }
+    if (n_out == 0 || n_w == 0 || n_h == 0 || n_w > N || r_w < n_w || r_h < n_h) return 0;
+    // unpad the needle rows (the bank API takes the tight canvas of ncc.rs:640)
+    std::vector<uint8_t> tight(n_w * n_h);
+    for (size_t y = 0; y < n_h; y++) memcpy(&tight[y * n_w], needle_u8 + y * N, n_w);
+    uint64_t off = 0;
+    uint16_t w16 = (uint16_t)n_w, h16 = (uint16_t)n_h;
+    focr_bank *bank = nullptr;
+    if (focr_bank_create(g_shim_ctx, tight.data(), &off, &w16, &h16, 1, &bank) != FOCR_OK) die("focr_bank_create");
+    // n_out may exceed what one sort can hold; the reference's callers use 1024 (ncc.rs:31,240)
+    const uint32_t n_out32 = (uint32_t)std::min<size_t>(n_out, 4096);
+    std::vector<focr_match> tmp(n_out32);
+    uint32_t cnt = 0;
+    int rc = scan_host_impl(g_shim_ctx, bank, reference, r_w * r_h, (uint32_t)r_w, (uint32_t)r_h, 1, threshold, n_out32,
+                            0 /* already inverted */, tmp.data(), &cnt);
+    focr_bank_destroy(bank);
+    if (rc != FOCR_OK) die("scan");
+    memcpy(out, tmp.data(), cnt * sizeof(focr_match));
+    return cnt;
+}
+
+extern "C" size_t ncc_8_u8(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t n_w, size_t n_h,
+                           uint32_t *, size_t, uint32_t *, double *, uint16_t *, float threshold, focr_match *out,
+                           size_t n_out)
+{
+    return shim_scan(reference, r_w, r_h, needle_u8, 8, n_w, n_h, threshold, out, n_out);
+}
+
+extern "C" size_t ncc_16_u8(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t n_w, size_t n_h,
+                            uint32_t *, size_t, uint32_t *, double *, uint16_t *, float threshold, focr_match *out,
+                            size_t n_out)
+{
+    return shim_scan(reference, r_w, r_h, needle_u8, 16, n_w, n_h, threshold, out, n_out);
+}

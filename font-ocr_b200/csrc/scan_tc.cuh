@@ -1,0 +1,34 @@
+// scan_tc.cuh -- host interface of the tcgen05 correlation kernel (scan_tc.cu).
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace focr {
+
+// per box size: the template bank re-laid out as the B operand of tcgen05.mma (K-major, no swizzle)
+struct TcClass {
+    bool supported = false;
+    uint32_t n_w = 0, n_h = 0, np = 0;
+    uint32_t n_tpl = 0;     // real templates of this class
+    uint32_t nb = 0;        // templates per N-block (multiple of 16, <= 256)
+    uint32_t n_blocks = 0;  // N-blocks
+    uint32_t kchunks = 0;   // 16-byte K chunks per template = n_h * np/16
+    uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
+    uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]
+    float2 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding/constant templates
+    uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
+};
+
+struct TcWorkspace {
+    void *work_counter = nullptr;  // device: dynamic tile scheduler counter
+};
+
+int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
+                   const uint32_t *bank_index, const TplInfo *info);
+void tc_class_release(TcClass &tc);
+bool tc_class_supported(const TcClass &tc);
+void tc_workspace_release(TcWorkspace &ws);
+cudaError_t launch_scan_tc(TcWorkspace &ws, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
+                           cudaStream_t st, int *n_launches);
+
+}  // namespace focr

@@ -1,0 +1,215 @@
+"""NCC template scan: Python mirror of the reference's host interface over the C ABI.
+
+Names follow ncc.rs: `Searcher` (ncc.rs:128-141,230-404), `get_hits` (ncc.rs:544-721),
+`process_hits` / `partition_by` (ncc.rs:723-786, 1036-1052).  The compute always happens in
+libfocr_b200.so (CUDA, sm_100a); there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import native
+from .native import MATCH_DTYPE, check, lib, ptr
+
+MAX_MATCHES = 1024  # ncc.rs:31
+
+
+class Context:
+    """focr_ctx: one per GPU."""
+
+    def __init__(self, device: int = 0, kernel: int = native.KERNEL_AUTO):
+        self._h = C.c_void_p()
+        check(lib().focr_ctx_create(device, C.byref(self._h)))
+        self.device = device
+        if kernel != native.KERNEL_AUTO:
+            self.set_kernel(kernel)
+
+    def set_kernel(self, kernel: int):
+        check(lib().focr_ctx_set_kernel(self._h, kernel))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().focr_ctx_stream(self._h) or 0)
+
+    def sync(self):
+        check(lib().focr_ctx_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().focr_ctx_launch_count(self._h))
+
+    def profile(self, enable: bool = True):
+        check(lib().focr_ctx_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{stage: (total ms, launches)} since the last read; synchronises."""
+        ms = np.zeros(4, np.float64)
+        n = np.zeros(4, np.uint64)
+        check(lib().focr_ctx_profile_read(self._h, ptr(ms), ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("invert", "stats", "scan", "finalize"))}
+
+    def close(self):
+        if self._h:
+            lib().focr_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Bank:
+    """focr_bank: the device-resident (glyph, subpixel shift) raster cache."""
+
+    def __init__(self, ctx: Context, templates):
+        """templates: sequence of u8 [n_h, n_w] arrays in the reference's (offset, letter) order."""
+        tpls = [np.ascontiguousarray(t, np.uint8) for t in templates]
+        self.ctx = ctx
+        self.sizes = [(t.shape[1], t.shape[0]) for t in tpls]
+        offsets = np.zeros(len(tpls), np.uint64)
+        o = 0
+        for i, t in enumerate(tpls):
+            offsets[i] = o
+            o += t.size
+        pixels = np.concatenate([t.ravel() for t in tpls]) if tpls else np.zeros(0, np.uint8)
+        n_w = np.array([s[0] for s in self.sizes], np.uint16)
+        n_h = np.array([s[1] for s in self.sizes], np.uint16)
+        self._h = C.c_void_p()
+        check(lib().focr_bank_create(ctx._h, ptr(pixels), ptr(offsets), ptr(n_w), ptr(n_h), len(tpls),
+                                     C.byref(self._h)))
+        self.T = len(tpls)
+
+    def close(self):
+        if self._h:
+            lib().focr_bank_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scan_pages(ctx: Context, bank: Bank, pages: np.ndarray, threshold: float = 0.8, n_out: int = MAX_MATCHES,
+               out: np.ndarray | None = None, counts: np.ndarray | None = None):
+    """focr_ncc_scan: pages u8 [P, r_h, r_w] gray (host).  Returns (matches [P, T, n_out], counts [P, T])."""
+    pages = np.ascontiguousarray(pages, np.uint8)
+    if pages.ndim == 2:
+        pages = pages[None]
+    P, r_h, r_w = pages.shape
+    if out is None:
+        out = np.zeros((P, bank.T, n_out), MATCH_DTYPE)
+    if counts is None:
+        counts = np.zeros((P, bank.T), np.uint32)
+    check(lib().focr_ncc_scan(ctx._h, bank._h, ptr(pages), r_w * r_h, r_w, r_h, P, C.c_float(threshold), n_out,
+                              ptr(out), ptr(counts)))
+    return out, counts
+
+
+def scan_pages_device(ctx: Context, bank: Bank, pages_ptr: int, page_stride: int, pitch: int, r_w: int, r_h: int,
+                      n_pages: int, threshold: float, n_out: int, out_ptr: int, counts_ptr: int):
+    """focr_ncc_scan_device on raw device addresses (e.g. torch tensors' data_ptr())."""
+    check(lib().focr_ncc_scan_device(ctx._h, bank._h, ptr(pages_ptr), page_stride, pitch, r_w, r_h, n_pages,
+                                     C.c_float(threshold), n_out, ptr(out_ptr), ptr(counts_ptr)))
+
+
+def window_stats(ctx: Context, page: np.ndarray, n_w: int, n_h: int):
+    page = np.ascontiguousarray(page, np.uint8)
+    r_h, r_w = page.shape
+    sp = np.zeros((r_h, r_w), np.uint32)
+    s2 = np.zeros((r_h, r_w), np.uint64)
+    rn = np.zeros((r_h, r_w), np.float64)
+    check(lib().focr_window_stats(ctx._h, ptr(page), r_w, r_h, n_w, n_h, ptr(sp), ptr(s2), ptr(rn)))
+    return sp, s2, rn
+
+
+def numerators(ctx: Context, bank: Bank, t: int, page: np.ndarray):
+    page = np.ascontiguousarray(page, np.uint8)
+    r_h, r_w = page.shape
+    acc = np.zeros((r_h, r_w), np.uint32)
+    check(lib().focr_ncc_numerators(ctx._h, bank._h, t, ptr(page), r_w, r_h, ptr(acc)))
+    return acc
+
+
+class Searcher:
+    """ncc.rs:128-141 `Searcher` through the compat shim: `search_c_u8` marshals exactly like
+    ncc.rs:332-404 and calls the library's `ncc_8_u8` / `ncc_16_u8` symbols."""
+
+    def __init__(self, gray: np.ndarray):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        self.r_h, self.r_w = gray.shape
+        self.reference_u8 = (255 - gray).astype(np.uint8)  # image_to_u8, ncc.rs:887-892
+        self.matches_c = np.zeros(MAX_MATCHES, MATCH_DTYPE)
+
+    def search_c_u8(self, needle: np.ndarray, threshold: float):
+        n_h, n_w = needle.shape
+        if n_w <= 8:
+            N, fn = 8, lib().ncc_8_u8
+        elif n_w <= 16:
+            N, fn = 16, lib().ncc_16_u8
+        else:
+            raise NotImplementedError("not handled")  # ncc.rs:392
+        padded = np.zeros((n_h, N), np.uint8)          # copy_needle_n_u8, ncc.rs:925-935
+        padded[:, :n_w] = needle
+        n = fn(ptr(self.reference_u8), self.r_w, self.r_h, ptr(padded), n_w, n_h, None, 0, None, None, None,
+               C.c_float(threshold), ptr(self.matches_c), MAX_MATCHES)
+        return self.matches_c[:n].copy()
+
+
+def partition_by(xs, pred):
+    """ncc.rs:1036-1052: groups are anchored to their FIRST element; panics on empty input."""
+    if len(xs) == 0:
+        raise IndexError("partition_by: empty input (the reference panics here, ncc.rs:1040)")
+    i = j = 0
+    last = xs[0]
+    out = []
+    for nxt in xs[1:]:
+        j += 1
+        if not pred(last, nxt):
+            out.append((i, j))
+            i = j
+            last = nxt
+    out.append((i, j + 1))
+    return out
+
+
+def get_hits(matches: np.ndarray, counts: np.ndarray, letters):
+    """Flatten one page's scan result into the reference's all_hits order (ncc.rs:675-681):
+    (template order, y, x) -> list of (letter, x, y, similarity)."""
+    out = []
+    for t, letter in enumerate(letters):
+        for m in matches[t, : counts[t]]:
+            out.append((letter, int(m["x"]), int(m["y"]), np.float32(m["similarity"])))
+    return out
+
+
+def process_hits(all_hits, anchor_threshold: float = 0.95, overlap: int = 5):
+    """ncc.rs:723-786 on (letter, x, y, similarity) tuples; returns lines of the same tuples."""
+    at = np.float32(anchor_threshold)
+    keep_y = {h[2] for h in all_hits if h[3] >= at}
+    hits = [h for h in all_hits if h[2] in keep_y]
+    hits.sort(key=lambda h: h[2])
+    slices = partition_by(hits, lambda a, b: a[2] == b[2])
+    for i, j in slices:
+        hits[i:j] = sorted(hits[i:j], key=lambda h: h[1])
+    lines = []
+    for i, j in slices:
+        sl = hits[i:j]
+        dedup = []
+        for a, b in partition_by(sl, lambda p, q: abs(p[1] - q[1]) <= overlap):
+            best = sl[a]
+            for h in sl[a + 1:b]:
+                if h[3] >= best[3]:  # Iterator::max_by keeps the LAST maximum
+                    best = h
+            dedup.append(best)
+        lines.append(dedup)
+    return lines
+
+
+def lines_to_text(lines):
+    return ["".join(h[0] for h in line) for line in lines]

@@ -1,0 +1,190 @@
+/*
+ * focr_b200.h -- C ABI of libfocr_b200.so, the B200 (sm_100a) drop-in for font-ocr's native hot path.
+ *
+ * What it replaces in the reference (all citations are into /root/reference/src):
+ *   - ncc.cpp:48-63 / ncc.cpp:253-268  `ncc_8_u8` / `ncc_16_u8`, bound by the Rust host through the
+ *     `unsafe extern "C"` block ncc.rs:92-126 and called from `Searcher::search_c_u8` ncc.rs:346-390.
+ *     Section 1 below exports THE SAME TWO SYMBOLS WITH THE SAME SIGNATURES, so the unmodified Rust
+ *     extern block links against this library.
+ *   - the per-(page, offset, letter) call loop of `get_hits` ncc.rs:587-702 around that kernel:
+ *     one kernel call per template is launch-bound on a GPU, so Section 2 is the batched form a
+ *     maintainer would switch `get_hits` to (INTEGRATION.md shows the Rust binding).
+ *   - `score_glyph` + `sum_of_squares` inside `decode_line` main.rs:87-181 (in-process Rust today,
+ *     no FFI): Section 3 is the new entry the focr binary would call.
+ *
+ * Conventions: plain C types only; no exceptions cross the boundary; every function that can
+ * fail returns an int status (FOCR_OK == 0) and leaves a message in focr_last_error().
+ * All buffers named `host` are caller-owned host memory that the callee borrows for the call
+ * (same ownership as the reference, ncc.rs:128-141,239-245).  Device memory, pinned staging and
+ * streams live inside the opaque context.  There is no CPU fallback: without a CUDA device every
+ * compute entry returns FOCR_ERR_CUDA.
+ */
+#ifndef FOCR_B200_H
+#define FOCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ncc.cpp:7-10 `struct Match` == ncc.rs:66-72 `MatchC` (#[repr(C)]): 8 bytes. */
+typedef struct focr_match {
+    uint16_t x, y;
+    float similarity;
+} focr_match;
+
+enum {
+    FOCR_OK = 0,
+    FOCR_ERR_CUDA = 1,        /* CUDA runtime/driver error or no device */
+    FOCR_ERR_ARG = 2,         /* NULL / zero-sized / inconsistent argument */
+    FOCR_ERR_UNSUPPORTED = 3, /* shape outside the supported range (see focr_limits) */
+    FOCR_ERR_NOMEM = 4
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Section 1 -- compat shim: the reference's FFI, symbol for symbol (ncc.cpp:48-63, 253-268).
+ *
+ * Semantics kept: `reference` is the INVERTED page (255 - gray, ncc.rs:887-892), r_w x r_h,
+ * row-major; `needle_u8` is N x n_h bytes (N = 8 resp. 16), rows zero-padded (ncc.rs:925-935);
+ * the scan covers y in [1, r_h-n_h], x in [1, r_w-n_w]; a window is a hit iff its f64 similarity
+ * is != +inf and > (double)threshold; hits are written in (y, x) raster order; when the n_out-th
+ * hit is written the call returns n_out at once (ncc.cpp:225-227); otherwise it returns the count.
+ * `acc`, `patch_sum`, `patch_rnorm` and `start_end` are accepted for signature compatibility and
+ * ignored (may be NULL): the window statistics are recomputed on the device from the page, which
+ * gives identical results because start/end only skip windows whose similarity is NaN
+ * (SURVEY.md section 8a K3).  Thread-safe (one internal context per device, serialised by a mutex).
+ * On a CUDA failure the shim prints the error to stderr and aborts, like the reference's
+ * `.unwrap()` call sites would on an impossible state -- it never returns a made-up count.
+ * ------------------------------------------------------------------------------------------ */
+size_t ncc_8_u8(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t n_w, size_t n_h,
+                uint32_t *acc, size_t acc_len, uint32_t *patch_sum, double *patch_rnorm,
+                uint16_t *start_end, float threshold, focr_match *out, size_t n_out);
+size_t ncc_16_u8(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t n_w, size_t n_h,
+                 uint32_t *acc, size_t acc_len, uint32_t *patch_sum, double *patch_rnorm,
+                 uint16_t *start_end, float threshold, focr_match *out, size_t n_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Section 2 -- batched NCC scan (replaces the loop ncc.rs:587-702 around search_c_u8).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct focr_ctx focr_ctx;   /* one per GPU; calls on one context are serialised by the caller */
+typedef struct focr_bank focr_bank; /* device-resident template bank == the (glyph, shift) raster cache */
+
+typedef struct focr_limits {
+    uint32_t max_template_w, max_template_h; /* ncc.rs:392 panics above 16; lifted here */
+    uint32_t max_page_w, max_page_h;         /* u16 coordinates, ncc.cpp:8 */
+    uint32_t max_n_out;
+} focr_limits;
+
+/* which correlation kernel a context uses */
+enum {
+    FOCR_KERNEL_AUTO = 0,  /* tcgen05 where the shape is supported, else SIMT */
+    FOCR_KERNEL_SIMT = 1,  /* dp4a kernel (scan_simt.cu) */
+    FOCR_KERNEL_TCGEN05 = 2 /* tcgen05 integer-MMA kernel (scan_tc.cu); FOCR_ERR_UNSUPPORTED if it cannot run the shape */
+};
+
+const char *focr_version(void);
+const char *focr_last_error(void); /* thread-local */
+void focr_get_limits(focr_limits *out);
+
+int focr_ctx_create(int device, focr_ctx **out);
+void focr_ctx_destroy(focr_ctx *ctx);
+int focr_ctx_set_kernel(focr_ctx *ctx, int kernel);
+/* the cudaStream_t all of this context's device work is enqueued on (for callers that time with
+ * CUDA events or interleave their own work) */
+void *focr_ctx_stream(focr_ctx *ctx);
+int focr_ctx_sync(focr_ctx *ctx);
+/* number of kernel launches this context has issued so far (bench.py's gpu_launches) */
+uint64_t focr_ctx_launch_count(const focr_ctx *ctx);
+/* Per-stage device timing: when enabled, CUDA events are recorded on the context's stream around
+ * each stage of the pipeline.  focr_ctx_profile_read synchronises, adds up the event intervals
+ * recorded since the last read into ms_out[FOCR_STAGE_*] / launches_out[FOCR_STAGE_*] and resets.
+ * This is how bench.py measures the correlation kernel's average launch duration live. */
+enum { FOCR_STAGE_INVERT = 0, FOCR_STAGE_STATS = 1, FOCR_STAGE_SCAN = 2, FOCR_STAGE_FINALIZE = 3, FOCR_N_STAGES = 4 };
+int focr_ctx_profile(focr_ctx *ctx, int enable);
+int focr_ctx_profile_read(focr_ctx *ctx, double *ms_out, uint64_t *launches_out);
+
+/* Upload a template bank.  Template i is the A8 canvas the reference's `render` (ncc.rs:143-196)
+ * returns: n_w[i] x n_h[i] bytes, rows tightly packed (stride n_w[i]), starting at
+ * pixels + offsets[i].  Order is the reference's iteration order (offset index, alphabet index,
+ * ncc.rs:587,630); every result below is indexed by this template index.  Templates may have
+ * different sizes (ncc.rs:600-626: the box can change with the subpixel offset); they are grouped
+ * by size internally. */
+int focr_bank_create(focr_ctx *ctx, const uint8_t *pixels, const uint64_t *offsets, const uint16_t *n_w,
+                     const uint16_t *n_h, uint32_t n_templates, focr_bank **out);
+void focr_bank_destroy(focr_bank *bank);
+uint32_t focr_bank_size(const focr_bank *bank);
+
+/* Scan n_pages pages of r_w x r_h GRAY pixels (what `image::open(..).into_luma8()` yields,
+ * ncc.rs:575; the library applies image_to_u8's 255-p itself) against every template of the bank.
+ * pages_host + p*page_stride is page p, rows tightly packed.
+ * out_host[(p*T + t)*n_out + k] is the k-th hit of template t on page p in the reference's
+ * emission order ((y, x) raster order, truncated at n_out exactly like ncc.cpp:225-227);
+ * counts_host[p*T + t] is what search_c_u8 would have got back as n_matches (== n_out when full).
+ * The timed end-to-end path: H2D of the pages, all kernels, D2H of the match lists. */
+int focr_ncc_scan(focr_ctx *ctx, const focr_bank *bank, const uint8_t *pages_host, size_t page_stride,
+                  uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
+                  focr_match *out_host, uint32_t *counts_host);
+
+/* Same scan with the pages already resident in device memory (gray, row pitch `pitch` bytes) and
+ * the results left in device memory; asynchronous on focr_ctx_stream().  This is what bench.py
+ * times as `value` (inputs in HBM when the timed region starts). */
+int focr_ncc_scan_device(focr_ctx *ctx, const focr_bank *bank, const uint8_t *pages_dev, size_t page_stride,
+                         size_t pitch, uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold,
+                         uint32_t n_out, focr_match *out_dev, uint32_t *counts_dev);
+
+/* Parity probes (tests/): the raw quantities north_star wants bit-exact.
+ * window stats for one page and one box size: s_p[y*r_w+x], s2_p[y*r_w+x] for x<=r_w-n_w, y<=r_h-n_h
+ * (other entries are left untouched); patch_rnorm as the reference's f64 plane (ncc.rs:306-312). */
+int focr_window_stats(focr_ctx *ctx, const uint8_t *page_gray_host, uint32_t r_w, uint32_t r_h, uint32_t n_w,
+                      uint32_t n_h, uint32_t *s_p_host, uint64_t *s2_p_host, double *patch_rnorm_host);
+/* raw correlation numerators acc[y*r_w+x] (ncc.cpp:108-166) of template t for one page */
+int focr_ncc_numerators(focr_ctx *ctx, const focr_bank *bank, uint32_t t, const uint8_t *page_gray_host,
+                        uint32_t r_w, uint32_t r_h, uint32_t *acc_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Section 3 -- focr least-squared-distance line decode (main.rs:87-181 on the device).
+ *
+ * The glyph bank is the (glyph, subpixel shift) raster cache README.md:44 asks for: for each glyph
+ * g < n_glyphs (alphabet order, main.rs:125-128) and each of the 64 horizontal 26.6 sub-pixel
+ * phases s, the FreeType bitmap of g at pen fraction s/64 with its placement relative to the
+ * integer pen position on the line canvas (left = bitmap_left, top = -bitmap_top + origin.y, both
+ * already including `origin` of main.rs:147).  advance_px[g] is
+ * `advance(g).x / units_per_em * size * kern_x` evaluated in f32 in that order (main.rs:176-178).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct focr_glyph_raster {
+    uint64_t offset;    /* into `pixels`: rows tightly packed, w*h bytes */
+    int16_t left, top;  /* top-left of the bitmap on the line canvas for integer pen x == 0 */
+    uint16_t w, h;
+} focr_glyph_raster;
+
+typedef struct focr_glyph_bank focr_glyph_bank;
+
+int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size_t n_pixel_bytes,
+                           const focr_glyph_raster *rasters /* [n_glyphs][64] */, const float *advance_px,
+                           uint32_t n_glyphs, focr_glyph_bank **out);
+void focr_glyph_bank_destroy(focr_glyph_bank *bank);
+
+/* Decode rectangles (x_start, y_start + i*line_advance, width, line_height), i = 0.. of each page
+ * exactly like decode_image main.rs:183-218: crop clamped to the page, stop at the first
+ * zero-height crop, skip all-white strips, stop at the first empty decode.
+ * glyphs_host[(p*max_lines + l)*max_cells + c] = alphabet index chosen for cell c of the l-th
+ * DECODED line of page p; n_cells_host[p*max_lines + l] its length; line_y_host[...] its y;
+ * n_lines_host[p] the number of decoded lines.  Lines beyond max_lines / cells beyond max_cells
+ * make the call fail with FOCR_ERR_ARG rather than truncate silently. */
+int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t *pages_host, size_t page_stride,
+                      uint32_t r_w, uint32_t r_h, uint32_t n_pages, uint32_t x_start, uint32_t y_start,
+                      uint32_t width, uint32_t line_height, uint32_t line_advance, uint32_t max_lines,
+                      uint32_t max_cells, uint16_t *glyphs_host, uint32_t *n_cells_host,
+                      uint32_t *line_y_host, uint32_t *n_lines_host);
+
+/* main.rs:510-516 `sum_of_squares` for n_pairs pairs of equal-length strips (parity probe; the
+ * decode kernel uses the algebraically identical Sum(ref^2) - 2*dot + Sum(g^2) form). */
+int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys_host, size_t len,
+                        uint32_t n_pairs, int64_t *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCR_B200_H */

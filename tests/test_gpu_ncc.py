@@ -1,0 +1,193 @@
+"""Parity of the CUDA NCC path with the oracle, through the C ABI (run on the B200: -m gpu).
+
+Bars (north_star): window sums and raw numerators bit-exact; match lists identical including order,
+the 1024 truncation and the f32 score bits (the 1e-5 tolerance north_star allows is not needed);
+post-processed text identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["simt", "tcgen05"])
+def kctx(request, ctx):
+    from font_ocr_b200 import native
+
+    ctx.set_kernel(native.KERNEL_SIMT if request.param == "simt" else native.KERNEL_TCGEN05)
+    yield ctx
+    ctx.set_kernel(native.KERNEL_AUTO)
+
+
+def _scan(kctx, templates, pages, thr, n_out=1024):
+    from font_ocr_b200 import native, ncc
+
+    bank = ncc.Bank(kctx, templates)
+    try:
+        return ncc.scan_pages(kctx, bank, pages, thr, n_out)
+    except native.FocrError as e:
+        if e.code == native.FOCR_ERR_UNSUPPORTED:
+            pytest.skip(f"kernel does not support this shape: {e}")
+        raise
+    finally:
+        bank.close()
+
+
+def _assert_same(matches, counts, expected_lists, tag=""):
+    for t, exp in enumerate(expected_lists):
+        c = int(counts[t])
+        assert c == len(exp), f"{tag} template {t}: count {c} != {len(exp)}"
+        got = matches[t, :c]
+        if got.tobytes() != exp.tobytes():
+            bad = [i for i in range(c) if got[i].tobytes() != exp[i].tobytes()]
+            raise AssertionError(f"{tag} template {t}: {len(bad)} of {c} differ, first {got[bad[0]]} vs {exp[bad[0]]}")
+
+
+def test_window_stats_bit_exact(ctx, oracle, golden):
+    from font_ocr_b200 import ncc
+
+    rng = np.random.default_rng(11)
+    cases = [(rng.integers(0, 256, (61, 97), dtype=np.uint8), [(5, 4), (16, 16), (1, 1), (32, 7)]),
+             (golden["text16_page"], [(15, 14), (8, 7), (27, 26)]),
+             (rng.integers(0, 256, (300, 700), dtype=np.uint8), [(32, 64), (13, 33)])]
+    for page, sizes in cases:
+        inv = (255 - page).astype(np.uint8)
+        for n_w, n_h in sizes:
+            sp, s2, rn = ncc.window_stats(ctx, page, n_w, n_h)
+            esp, es2 = oracle.window_sums(inv, n_w, n_h)
+            ys, xs = esp.shape
+            assert np.array_equal(sp[:ys, :xs], esp), (n_w, n_h)
+            assert np.array_equal(s2[:ys, :xs], es2), (n_w, n_h)
+            with np.errstate(all="ignore"):  # ncc.rs:309-311 in IEEE f64
+                ern = 1.0 / np.sqrt(es2.astype(np.float64) - (esp * esp).astype(np.float64) / float(n_w * n_h))
+            assert np.array_equal(rn[:ys, :xs], ern), (n_w, n_h)
+
+
+def test_numerators_bit_exact(ctx, oracle, golden):
+    from font_ocr_b200 import ncc
+
+    page, tpl = golden["text16_page"], golden["text16_tpl"]
+    rng = np.random.default_rng(5)
+    noise = rng.integers(0, 256, (90, 200), dtype=np.uint8)
+    wide = rng.integers(0, 256, (26, 27), dtype=np.uint8)
+    for pg, templates in ((page, [tpl[0], tpl[40]]), (noise, [tpl[3], wide, wide[:3, :20]])):
+        bank = ncc.Bank(ctx, templates)
+        inv = (255 - pg).astype(np.uint8)
+        for t, tp in enumerate(templates):
+            acc = ncc.numerators(ctx, bank, t, pg)
+            win = np.lib.stride_tricks.sliding_window_view(inv, tp.shape)
+            exp = np.einsum("yxij,ij->yx", win.astype(np.int64), tp.astype(np.int64))
+            ys, xs = exp.shape
+            assert np.array_equal(acc[1:ys, 1:xs], exp[1:, 1:]), t  # row/col 0 are never searched
+        bank.close()
+
+
+def test_scan_matches_golden_text(kctx, golden):
+    for name in ("text16", "text8"):
+        m, c = _scan(kctx, list(golden[f"{name}_tpl"]), golden[f"{name}_page"], float(golden[f"{name}_thr"]))
+        exp, off = [], 0
+        for n in golden[f"{name}_counts"]:
+            exp.append(golden[f"{name}_hits"][off:off + n])
+            off += n
+        _assert_same(m[0], c[0], exp, name)
+
+
+def test_scan_matches_golden_truncation(kctx, golden):
+    n_out = int(golden["noise_n_out"])
+    tpls = [golden[f"noise_tpl{i}"] for i in range(int(golden["noise_n"]))]
+    m, c = _scan(kctx, tpls, golden["noise_page"], float(golden["noise_thr"]), n_out)
+    _assert_same(m[0], c[0], [golden[f"noise_hits{i}"] for i in range(len(tpls))], "noise")
+    m, c = _scan(kctx, [golden["dense_tpl"]], golden["dense_page"], float(golden["dense_thr"]))
+    assert c[0, 0] == 1024  # ncc.cpp:225-227: full -> returns n_out
+    _assert_same(m[0], c[0], [golden["dense_hits"]], "dense")
+
+
+def test_scan_random_vs_oracle(kctx, oracle):
+    rng = np.random.default_rng(2024)
+    for trial in range(10):
+        h, w = int(rng.integers(40, 200)), int(rng.integers(40, 300))
+        page = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        if trial % 2 == 0:
+            page[rng.random((h, w)) < 0.8] = 255
+        if trial % 3 == 0:
+            page[10:30, 5:35] = 0  # a saturated block: constant non-zero windows
+        n_w, n_h = int(rng.integers(1, 33)), int(rng.integers(1, 33))
+        tpls = [rng.integers(0, 256, (n_h, n_w), dtype=np.uint8) for _ in range(int(rng.integers(1, 40)))]
+        tpls[0][:] = 0  # an all-zero template (e.g. space): NaN similarity everywhere -> no hits
+        if len(tpls) > 2:
+            tpls[1][:] = 77  # a constant template: rnorm_n = inf
+        thr = float(rng.choice([0.1, 0.2, 0.5]))
+        n_out = int(rng.choice([16, 1024]))
+        m, c = _scan(kctx, tpls, page, thr, n_out)
+        s = oracle.Searcher(page, "port")
+        exp = [s.search_c_u8(t, thr, n_out=n_out, allow_wide=True) for t in tpls]
+        _assert_same(m[0], c[0], exp, f"trial {trial} box {n_w}x{n_h}")
+
+
+def test_mixed_size_bank_and_batch(kctx, oracle, font, pkg):
+    """--x-bits 2 --y-bits 2 at -t 7: four box sizes in one bank (ncc.rs:600-626); three pages per call."""
+    bank = pkg.raster.TemplateBank(font, 7, x_bits=2, y_bits=2)
+    assert len(bank.sizes()) > 1
+    tpls = [t.pixels for t in bank.templates]
+    pages = np.stack([pkg.pages.make_ncc_page(bank, 304, 200, seed=s, margin_x=11, margin_y=9, shifts="bank")[0]
+                      for s in range(3)])
+    m, c = _scan(kctx, tpls, pages, 0.8)
+    for p in range(3):
+        exp = oracle.get_hits(pages[p], tpls, 0.8, "port")
+        _assert_same(m[p], c[p], exp, f"page {p}")
+
+
+def test_shim_is_the_reference_ffi(ctx, golden):
+    """Searcher.search_c_u8 marshals like ncc.rs:332-404 and calls the exported ncc_8_u8/ncc_16_u8."""
+    from font_ocr_b200 import ncc
+
+    s = ncc.Searcher(golden["text16_page"])
+    off = 0
+    for t in range(0, 74, 9):
+        n = int(golden["text16_counts"][t])
+        off = int(golden["text16_counts"][:t].sum())
+        got = s.search_c_u8(golden["text16_tpl"][t], 0.8)
+        assert got.tobytes() == golden["text16_hits"][off:off + n].tobytes(), t
+    s8 = ncc.Searcher(golden["text8_page"])
+    got = s8.search_c_u8(golden["text8_tpl"][5], 0.8)
+    off = int(golden["text8_counts"][:5].sum())
+    assert got.tobytes() == golden["text8_hits"][off:off + int(golden["text8_counts"][5])].tobytes()
+
+
+def test_decoded_text_identical(kctx, oracle, golden):
+    from font_ocr_b200 import ncc
+
+    letters = list(golden["text16_letters"])
+    m, c = _scan(kctx, list(golden["text16_tpl"]), golden["text16_page"], 0.8)
+    ours = ncc.lines_to_text(ncc.process_hits(ncc.get_hits(m[0], c[0], letters)))
+    ref_hits = oracle.get_hits(golden["text16_page"], list(golden["text16_tpl"]), 0.8, "port")
+    theirs = oracle.lines_to_text(oracle.process_hits(oracle.hits_with_letters(ref_hits, letters)))
+    assert ours == theirs
+    truth = list(golden["text16_lines"])
+    assert sum(a == b for a, b in zip(ours, truth)) >= len(truth) - 3
+
+
+def test_full_size_page_properties_and_sample(kctx, oracle, font, pkg):
+    """BASELINE config 3 shape: 2480x3508, --x-bits 2 (296 templates).  The oracle checks a sample of
+    templates exactly (the compiled reference when present); size-independent properties cover the rest:
+    raster order, the 1024 cap, every score above the threshold, idempotence."""
+    bank = pkg.raster.TemplateBank(font, 13, x_bits=2)
+    tpls = [t.pixels for t in bank.templates]
+    page = pkg.pages.make_ncc_page(bank, 2480, 3508, seed=3, shifts="bank")[0]
+    m, c = _scan(kctx, tpls, page, 0.8)
+    m2, c2 = _scan(kctx, tpls, page, 0.8)
+    assert np.array_equal(c, c2) and m.tobytes() == m2.tobytes()  # deterministic despite atomics
+    assert c.max() == 1024 and (c <= 1024).all()
+    for t in range(len(tpls)):
+        g = m[0, t, :c[0, t]]
+        key = g["y"].astype(np.int64) * 65536 + g["x"]
+        assert (np.diff(key) > 0).all(), t
+        assert (g["similarity"] > np.float32(0.8) - 1e-6).all()
+        n_h, n_w = tpls[t].shape
+        assert (g["x"] >= 1).all() and (g["y"] >= 1).all()
+        assert (g["x"] <= 2480 - n_w).all() and (g["y"] <= 3508 - n_h).all()
+    impl = "reference" if oracle.ref_lib() is not None else "port"
+    s = oracle.Searcher(page, impl)
+    sample = list(range(0, len(tpls), 37)) if impl == "reference" else [0, 150]
+    for t in sample:
+        exp = s.search_c_u8(tpls[t], 0.8)
+        _assert_same(m[0, t:t + 1], c[0, t:t + 1], [exp], f"template {t}")
