@@ -749,7 +749,17 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     a.sink.r_h = r_h;
     a.acc_out = s.acc.as<uint32_t>();
     int nl = 0;
-    CU(launch_scan_simt(a, 1, st, &nl));
+    if (c->kernel == FOCR_KERNEL_TCGEN05) {
+        // same probe through the tcgen05 kernel: the whole class runs, column `pos` is dumped from TMEM
+        if (!tc_class_supported(ch.tc)) return fail(FOCR_ERR_UNSUPPORTED, "tcgen05 kernel does not support this box");
+        a.cls.n_tpl = (uint32_t)ch.index.size();
+        a.cls.tpl_index = ch.index_dev.as<uint32_t>();
+        a.cls.rows = ch.rows.as<uint8_t>();
+        a.acc_out = nullptr;
+        CU(launch_scan_tc(c->tc, ch.tc, a, 1, c->sm_count, st, &nl, s.acc.as<uint32_t>(), (int)pos));
+    } else {
+        CU(launch_scan_simt(a, 1, st, &nl));
+    }
     c->launches += 2 + nl;
     CU(cudaMemcpyAsync(acc_host, s.acc.p, page_bytes * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

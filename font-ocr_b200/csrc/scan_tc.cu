@@ -1,18 +1,611 @@
-// scan_tc.cu -- placeholder until the tcgen05 kernel lands (next commit): reports "unsupported"
-// so FOCR_KERNEL_AUTO takes the SIMT kernel.
+// scan_tc.cu -- the NCC correlation as a tcgen05 integer-MMA GEMM (sm_100a), with an exact epilogue.
+//
+// Replaces the hot loops of ncc_8_u8 / ncc_16_u8 (ncc.cpp:98-248, 302-393) for ALL templates of one
+// box size at once.  For an output row y of a 128-window strip,
+//
+//     D[m, t] = sum_{ny, j} page[y+ny][x0+m+j] * tpl[t][ny][j]          (exact, u8 x u8 -> s32)
+//
+// is a GEMM with M = 128 windows, N = NB templates (<= 256) and K = 16*n_h (32*n_h for boxes wider
+// than 16): A is the Toeplitz (im2col) expansion of the page rows, B the template bank.
+//
+// * A cannot be described by a UMMA shared-memory descriptor directly (rows of a core matrix are 16 B
+//   apart, windows are 1 B apart), so every page row is expanded ONCE into a 128 x 16 B block in shared
+//   memory and then reused by all n_h vertical taps and all NB templates: the k-th MMA of a row simply
+//   points its descriptor at ring slots (y+2k, y+2k+1) through the leading-dimension byte offset.
+// * Raw page rows arrive by TMA bulk copies (cp.async.bulk, mbarrier complete_tx).
+// * B (templates, K-major, no swizzle) is loaded once per launch by one bulk copy.
+// * Accumulators live in TMEM (double/quad buffered); one elected thread issues tcgen05.mma kind::i8.
+// * Epilogue (8 warps): tcgen05.ld -> fp32 prefilter with a proven safety margin -> the reference's
+//   exact f64 normalisation (ncc.cpp:212-220) only for the survivors -> warp-aggregated atomic append.
+//   The integer numerators are exact, the decision and the f32 score are bit-identical to the CPU.
+//
+// Warp roles (512 threads, one CTA per SM, persistent over (page, x-strip, y-segment) items):
+//   warp 0      TMA producer of raw page rows          warp 1   MMA issuer
+//   warp 2      TMEM allocator                         warp 3   idle
+//   warps 4-7   Toeplitz expansion (thread = window)   warps 8-15  epilogue (two column halves)
+#include <cooperative_groups.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "scan_tc.cuh"
+
+namespace cg = cooperative_groups;
+
 namespace focr {
-int tc_class_build(TcClass &tc, const uint8_t *, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
-                   const uint32_t *, const TplInfo *)
+
+constexpr int TC_THREADS = 512;
+constexpr int TC_RAW_SLOTS = 8;       // raw page-row ring (TMA destination), 160 B each
+constexpr int TC_RAW_BYTES = 160;
+constexpr int TC_LOOK = 6;            // expanded rows the producer side may run ahead of the MMA
+constexpr int TC_RING_MAX = 40;       // max ring slots (n_hp + TC_LOOK)
+constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
+constexpr int TC_YSEG = 128;          // output rows per work item
+constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+    const uint8_t *inv;
+    size_t inv_page_stride;
+    int pitch, r_w, r_h;
+    int n_w, n_h, np;
+    int n_hp;          // page rows an output row needs (n_h rounded up to 2 when np == 16)
+    int ksteps;        // tcgen05.mma per output row
+    int nb;            // N of the MMA (templates per launch, multiple of 16)
+    int nbs;           // TMEM column stride between accumulator buffers (nb rounded up to 32)
+    int nbuf;          // accumulator buffers
+    int ring;          // ring slots
+    int row_pitch;     // bytes per expanded row slot
+    int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
+    int nch, nch0;     // 32-column chunks in total / handled by epilogue half 0
+    const uint8_t *btile;    // [2*ksteps][nb][16]
+    uint32_t btile_bytes;
+    const uint32_t *tpl_of;  // [nb] bank index of each column (0xFFFFFFFF = padding)
+    const TplInfo *tpl;
+    const uint32_t *sp;
+    const uint32_t *s2p;
+    const float *pf;
+    int spitch;
+    size_t plane_page_stride;
+    double thr_d;
+    HitSink sink;
+    int n_pages, n_xstrips, n_ysegs;
+    uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x] (NULL in production)
+    int dbg_col;
+    // prefilter constants per column, negated: {-a', -b'}; half h covers columns (h ? nch0*32 : 0) + j
+    float2 cst[2][128];
+};
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    tc.supported = false; tc.n_w = n_w; tc.n_h = n_h; tc.np = np; tc.n_tpl = n_tpl;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
+//   core matrix = 8 rows x 16 B, rows 16 B apart; 8-row groups SBO apart; the two 16-B K chunks LBO apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);  // version = 1 (Blackwell), base_offset = 0, lbo_mode = 0, layout = SWIZZLE_NONE
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
+{
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------- work items
+struct Item {
+    int page, x0, ys0, ys1;
+};
+__device__ __forceinline__ bool get_item(const TcParams &p, int idx, Item &it)
+{
+    const int per_page = p.n_xstrips * p.n_ysegs;
+    if (idx >= p.n_pages * per_page) return false;
+    it.page = idx / per_page;
+    const int r = idx - it.page * per_page;
+    const int ys = r / p.n_xstrips, xs = r - ys * p.n_xstrips;
+    it.x0 = xs * 128;
+    it.ys0 = 1 + ys * TC_YSEG;  // ncc.cpp:98: the scan starts at y = 1
+    it.ys1 = min(it.ys0 + TC_YSEG, p.r_h - p.n_h + 1);
+    return true;
+}
+
+// the rare path: the reference's exact arithmetic for one prefilter survivor
+__device__ __noinline__ void exact_check(const TcParams &p, uint32_t acc, uint32_t col, uint32_t s_p, size_t plane_off,
+                                         int page, int gx, int y)
+{
+    const uint32_t t = p.tpl_of[col];
+    if (t == 0xFFFFFFFFu) return;
+    const TplInfo ti = p.tpl[t];
+    const uint32_t s2_p = p.s2p[plane_off];
+    const double rn_p = patch_rnorm(s_p, s2_p, (double)(p.n_w * p.n_h));
+    float sim;
+    if (ncc_exact(acc, s_p, rn_p, ti.s_n, ti.n_recip, ti.rnorm_n, p.thr_d, &sim)) {
+        // warp-aggregated append: one atomic per group of simultaneously hitting lanes
+        auto g = cg::coalesced_threads();
+        unsigned base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(p.sink.hit_count, (unsigned)g.size());
+        base = g.shfl(base, 0);
+        const unsigned slot = base + g.thread_rank();
+        if (slot < p.sink.hit_cap) {
+            Hit h;
+            h.t = t;
+            h.yx = ((uint32_t)y << 16) | (uint32_t)gx;
+            h.sim = sim;
+            h.page = page;
+            p.sink.hits[slot] = h;
+        }
+        atomicAdd(p.sink.rowcount + ((size_t)page * p.sink.T + t) * p.sink.r_h + y, 1u);
+    }
+}
+
+// one 32-column chunk of the prefilter: bit (31-j) of the result is the SIGN of
+//   d_j = acc_j - b'_j*S - a'_j*P        (a', b' shrunk by 2^-12: see DESIGN.md "prefilter margin")
+// i.e. a 0 bit marks a candidate.  H selects the constant table so that every constant is a
+// compile-time offset into the kernel parameter bank (no loads in the loop).
+template <int H, int CH>
+__device__ __forceinline__ uint32_t prefilter_chunk(const TcParams &p, const uint32_t (&v)[32], float S, float P)
+{
+    uint32_t m0 = 0, m1 = 0;  // two interleaved chains halve the dependency depth
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float2 c0 = p.cst[H][CH * 32 + j], c1 = p.cst[H][CH * 32 + j + 1];
+        float d0 = __fmaf_rn(c0.y, S, __int2float_rn((int)v[j]));
+        float d1 = __fmaf_rn(c1.y, S, __int2float_rn((int)v[j + 1]));
+        d0 = __fmaf_rn(c0.x, P, d0);
+        d1 = __fmaf_rn(c1.x, P, d1);
+        m0 = __funnelshift_l(__float_as_uint(d0), m0, 1);
+        m1 = __funnelshift_l(__float_as_uint(d1), m1, 1);
+    }
+    // interleave back: column j even -> m0 bit (15 - j/2), odd -> m1 bit (15 - j/2); callers only need
+    // "which columns", so return both halves packed: high 16 bits = even columns, low 16 = odd columns
+    return (m0 << 16) | (m1 & 0xFFFFu);
+}
+
+template <int H>
+__device__ __forceinline__ void epilogue_row(const TcParams &p, uint32_t tbase, int nchunks, int col0, float S, float P,
+                                             bool valid, uint32_t s_p, size_t plane_off, int page, int gx, int y)
+{
+    // tbase already includes the lane quarter and the buffer's first column
+#define FOCR_CHUNK(CH)                                                                                    \
+    if (CH < nchunks) {                                                                                   \
+        uint32_t v[32];                                                                                   \
+        tc_ld32(tbase + col0 + CH * 32, v);                                                               \
+        tc_wait_ld();                                                                                     \
+        uint32_t sign = prefilter_chunk<H, CH>(p, v, S, P);                                               \
+        uint32_t cand = valid ? ~sign : 0u;                                                               \
+        uint32_t any = __reduce_or_sync(0xffffffffu, cand);                                               \
+        while (any) {                                                                                     \
+            const int b = 31 - __clz(any);                                                                \
+            any &= ~(1u << b);                                                                            \
+            /* bit b: b >= 16 -> even column 2*(31-b), else odd column 2*(15-b)+1 */                      \
+            const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;                                      \
+            const uint32_t a = tc_ld1(tbase + col0 + CH * 32 + j);                                        \
+            tc_wait_ld();                                                                                 \
+            if ((cand >> b) & 1u) exact_check(p, a, col0 + CH * 32 + j, s_p, plane_off, page, gx, y);     \
+        }                                                                                                 \
+    }
+    FOCR_CHUNK(0)
+    FOCR_CHUNK(1)
+    FOCR_CHUNK(2)
+    FOCR_CHUNK(3)
+#undef FOCR_CHUNK
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // ---- shared memory carve-up
+    uint8_t *btile = smem;
+    uint8_t *ring = btile + ((p.btile_bytes + 127) & ~127u);
+    uint8_t *raw = ring + (size_t)(p.ring + 1) * p.row_pitch;  // +1: mirror of slot 0 for (ring-1, 0) pairs
+    uint64_t *bars = (uint64_t *)(raw + TC_RAW_SLOTS * TC_RAW_BYTES);
+    uint64_t *bar_btile = bars;                       // 1
+    uint64_t *raw_full = bars + 1;                    // TC_RAW_SLOTS
+    uint64_t *raw_empty = raw_full + TC_RAW_SLOTS;    // TC_RAW_SLOTS
+    uint64_t *a_full = raw_empty + TC_RAW_SLOTS;      // TC_RING_MAX
+    uint64_t *a_empty = a_full + TC_RING_MAX;         // TC_RING_MAX
+    uint64_t *t_full = a_empty + TC_RING_MAX;         // TC_MAX_BUF
+    uint64_t *t_empty = t_full + TC_MAX_BUF;          // TC_MAX_BUF
+    uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_btile, 1);
+        for (int i = 0; i < TC_RAW_SLOTS; i++) {
+            mbar_init(raw_full + i, 1);
+            mbar_init(raw_empty + i, 128);
+        }
+        for (int i = 0; i < TC_RING_MAX; i++) {
+            mbar_init(a_full + i, 128);
+            mbar_init(a_empty + i, 1);
+        }
+        for (int i = 0; i < TC_MAX_BUF; i++) {
+            mbar_init(t_full + i, 1);
+            mbar_init(t_empty + i, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_btile, p.btile_bytes);
+            tma_bulk_g2s(btile, p.btile, p.btile_bytes, bar_btile);
+            const uint32_t row_bytes = 128 + p.np;
+            uint32_t g = 0;  // raw rows produced so far
+            Item it;
+            for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+                const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0;
+                const int y_end = it.ys1 + p.n_hp - 1;
+                for (int y = it.ys0; y < y_end; y++, g++) {
+                    const uint32_t s = g % TC_RAW_SLOTS;
+                    if (g >= TC_RAW_SLOTS) mbar_wait(raw_empty + s, ((g / TC_RAW_SLOTS) - 1) & 1);
+                    mbar_arrive_expect_tx(raw_full + s, row_bytes);
+                    tma_bulk_g2s(raw + s * TC_RAW_BYTES, src + (size_t)y * p.pitch, row_bytes, raw_full + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4)                      // D format: S32
+                                   | (0u << 7) | (0u << 10)       // A, B: unsigned 8-bit
+                                   | (0u << 15) | (0u << 16)      // A, B: K-major
+                                   | ((uint32_t)(p.nb >> 3) << 17)  // N
+                                   | ((128u >> 4) << 24);         // M = 128
+            const uint32_t b_lbo = (uint32_t)p.nb * 16u;
+            const uint32_t a_lbo = p.np == 16 ? (uint32_t)p.row_pitch : 256u;
+            const uint32_t ring_addr = smem_u32(ring), btile_addr = smem_u32(btile);
+            mbar_wait(bar_btile, 0);
+            uint32_t g0 = 0;  // expanded-row index of the current item's first row
+            uint32_t job = 0;  // output rows issued so far (accumulator buffer sequence)
+            Item it;
+            for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+                const int n_out_rows = it.ys1 - it.ys0;
+                for (int j = 0; j < n_out_rows; j++, job++) {
+                    // the newest row this output needs (expansion is in order, so older rows are done)
+                    const uint32_t gl = g0 + j + p.n_hp - 1;
+                    mbar_wait(a_full + gl % p.ring, (gl / p.ring) & 1);
+                    const uint32_t buf = job % p.nbuf;
+                    if (job >= (uint32_t)p.nbuf) mbar_wait(t_empty + buf, ((job / p.nbuf) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * p.nbs;
+                    for (int k = 0; k < p.ksteps; k++) {
+                        uint32_t a_addr;
+                        if (p.np == 16) {
+                            const uint32_t s = (g0 + j + 2 * k) % p.ring;  // pair (s, s+1); slot `ring` mirrors slot 0
+                            a_addr = ring_addr + s * p.row_pitch;
+                        } else {
+                            const uint32_t s = (g0 + j + k) % p.ring;      // chunks 0 and 1 of one row, 16 windows apart
+                            a_addr = ring_addr + s * p.row_pitch;
+                        }
+                        const uint64_t adesc = make_desc(a_addr, a_lbo, 128);
+                        const uint64_t bdesc = make_desc(btile_addr + (uint32_t)(2 * k) * b_lbo, b_lbo, 128);
+                        tc_mma_i8(d_tmem, adesc, bdesc, idesc, k > 0);
+                    }
+                    tc_commit(t_full + buf);                       // accumulator ready for the epilogue
+                    tc_commit(a_empty + (g0 + j) % p.ring);        // row g0+j is not needed by later outputs
+                }
+                // the last n_hp-1 rows of the item are never the first row of an output: release them too
+                for (int j = n_out_rows; j < n_out_rows + p.n_hp - 1; j++) tc_commit(a_empty + (g0 + j) % p.ring);
+                g0 += n_out_rows + p.n_hp - 1;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================================================== Toeplitz expansion
+        const int e = threadIdx.x - 128;  // window index 0..127
+        const bool mirror = p.np == 16;
+        uint32_t g = 0;
+        Item it;
+        for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+            const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
+            for (int r = 0; r < n_rows; r++, g++) {
+                const uint32_t rs = g % TC_RAW_SLOTS, s = g % p.ring;
+                mbar_wait(raw_full + rs, (g / TC_RAW_SLOTS) & 1);
+                if (g >= (uint32_t)p.ring) mbar_wait(a_empty + s, ((g / p.ring) - 1) & 1);
+                const uint32_t *rw = (const uint32_t *)(raw + rs * TC_RAW_BYTES);
+                uint8_t *dst = ring + (size_t)s * p.row_pitch;
+                for (int ee = e; ee < p.n_entries; ee += 128) {
+                    const uint32_t *w = rw + (ee >> 2);
+                    const int sh = (ee & 3) * 8;
+                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                    uint4 o;
+                    o.x = __funnelshift_r(w0, w1, sh);
+                    o.y = __funnelshift_r(w1, w2, sh);
+                    o.z = __funnelshift_r(w2, w3, sh);
+                    o.w = __funnelshift_r(w3, w4, sh);
+                    *(uint4 *)(dst + ee * 16) = o;
+                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)p.ring * p.row_pitch + ee * 16) = o;
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+                mbar_arrive(a_full + s);
+                mbar_arrive(raw_empty + rs);
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================================================== epilogue
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int half = (warp - 8) >> 2;  // column half
+        const int m = q * 32 + lane;       // window within the strip
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int col0 = half ? p.nch0 * 32 : 0;
+        const int nchunks = half ? p.nch - p.nch0 : p.nch0;
+        uint32_t job = 0;
+        Item it;
+        for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+            const int gx = it.x0 + m;
+            const bool x_ok = gx >= 1 && gx <= p.r_w - p.n_w;  // ncc.rs:281: x starts at 1
+            const size_t plane = (size_t)it.page * p.plane_page_stride + gx;
+            uint32_t s_p = 0;
+            float P = 0.f;
+            if (x_ok) {
+                s_p = __ldg(p.sp + plane + (size_t)it.ys0 * p.spitch);
+                P = __ldg(p.pf + plane + (size_t)it.ys0 * p.spitch);
+            }
+            for (int y = it.ys0; y < it.ys1; y++, job++) {
+                // prefetch the next row's window statistics
+                uint32_t s_next = 0;
+                float P_next = 0.f;
+                if (x_ok && y + 1 < it.ys1) {
+                    s_next = __ldg(p.sp + plane + (size_t)(y + 1) * p.spitch);
+                    P_next = __ldg(p.pf + plane + (size_t)(y + 1) * p.spitch);
+                }
+                const bool valid = x_ok && P < __int_as_float(0x7f800000);  // +inf marks a constant window
+                const float S = (float)s_p;
+                const float Pv = valid ? P : 0.f;
+                const uint32_t buf = job % p.nbuf;
+                mbar_wait(t_full + buf, (job / p.nbuf) & 1);
+                tc_fence_after();
+                const uint32_t tb = tlane + buf * p.nbs;
+                const size_t plane_off = plane + (size_t)y * p.spitch;
+                if (half == 0)
+                    epilogue_row<0>(p, tb, nchunks, col0, S, Pv, valid, s_p, plane_off, it.page, gx, y);
+                else
+                    epilogue_row<1>(p, tb, nchunks, col0, S, Pv, valid, s_p, plane_off, it.page, gx, y);
+                if (p.dbg_acc && p.dbg_col >= col0 && p.dbg_col < col0 + nchunks * 32) {
+                    const uint32_t a = tc_ld1(tb + p.dbg_col);
+                    tc_wait_ld();
+                    if (x_ok) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + buf);
+                s_p = s_next;
+                P = P_next;
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int row_pitch)
+{
+    return ((btile_bytes + 127) & ~127u) + (size_t)(ring + 1) * row_pitch + TC_RAW_SLOTS * TC_RAW_BYTES +
+           (1 + 2 * TC_RAW_SLOTS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 16;
+}
+
+int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
+                   const uint32_t *bank_index, const TplInfo *info)
+{
+    tc.supported = false;
+    tc.n_w = n_w;
+    tc.n_h = n_h;
+    tc.np = np;
+    tc.n_tpl = n_tpl;
+    const uint32_t n_hp = np == 16 ? (n_h + 1) & ~1u : n_h;
+    tc.kchunks = n_h * (np / 16);
+    tc.ksteps = (tc.kchunks + 1) / 2;
+    const int ring = (int)n_hp + TC_LOOK;
+    const int row_pitch = np == 16 ? 2048 : 2304;
+    if (ring > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
+    // largest NB (multiple of 16, <= 256) whose B tile fits next to the ring
+    int nb_max = 256;
+    while (nb_max >= 16 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, row_pitch) > TC_SMEM_BUDGET) nb_max -= 16;
+    if (nb_max < 16) return 0;
+    tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
+    tc.nb = ((n_tpl + tc.n_blocks - 1) / tc.n_blocks + 15) & ~15u;
+    const size_t tile = (size_t)2 * tc.ksteps * tc.nb * 16;
+    std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
+    std::vector<float2> cst((size_t)tc.n_blocks * tc.nb);
+    std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
+    const float inf = INFINITY;
+    for (auto &c : cst) c = make_float2(inf, 0.f);
+    for (uint32_t i = 0; i < n_tpl; i++) {
+        const uint32_t blk = i / tc.nb, n = i % tc.nb;
+        for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
+            const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
+            memcpy(&bt[blk * tile + ((size_t)kc * tc.nb + n) * 16], rows_host + ((size_t)i * n_h + row) * np + boff, 16);
+        }
+        const TplInfo &ti = info[i];
+        // norm_n = sqrt(s2_n - s_n^2/n) = 1/rnorm_n ; constant (incl. all-zero) templates can never hit
+        const double norm_n = 1.0 / ti.rnorm_n;
+        const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
+        cst[(size_t)blk * tc.nb + n] = make_float2(ok ? (float)norm_n : inf, (float)(ti.s_n * ti.n_recip));
+        tof[(size_t)blk * tc.nb + n] = bank_index[i];
+    }
+    if (cudaMalloc(&tc.b_tiles, bt.size()) != cudaSuccess) return -1;
+    if (cudaMalloc(&tc.tpl_of, tof.size() * 4) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.b_tiles, bt.data(), bt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.tpl_of, tof.data(), tof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    tc.consts_host = new std::vector<float2>(std::move(cst));
+    tc.supported = true;
     return 0;
 }
-void tc_class_release(TcClass &) {}
+
+void tc_class_release(TcClass &tc)
+{
+    if (tc.b_tiles) cudaFree(tc.b_tiles);
+    if (tc.consts) cudaFree(tc.consts);
+    if (tc.tpl_of) cudaFree(tc.tpl_of);
+    delete (std::vector<float2> *)tc.consts_host;
+    tc.b_tiles = nullptr;
+    tc.consts = nullptr;
+    tc.tpl_of = nullptr;
+    tc.consts_host = nullptr;
+    tc.supported = false;
+}
+
 bool tc_class_supported(const TcClass &tc) { return tc.supported; }
 void tc_workspace_release(TcWorkspace &) {}
-cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &, const ScanArgs &, int, int, cudaStream_t, int *)
+
+cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
+                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc, int dbg_pos)
 {
-    return cudaErrorNotSupported;
+    if (!tc.supported) return cudaErrorNotSupported;
+    thread_local TcParams p;  // 2.3 KB: keep it off the stack
+    p.inv = a.inv;
+    p.inv_page_stride = a.inv_page_stride;
+    p.pitch = a.pitch;
+    p.r_w = a.r_w;
+    p.r_h = a.r_h;
+    p.n_w = tc.n_w;
+    p.n_h = tc.n_h;
+    p.np = tc.np;
+    p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
+    p.ksteps = tc.ksteps;
+    p.nb = tc.nb;
+    p.nbs = (tc.nb + 31) & ~31;
+    p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
+    p.ring = p.n_hp + TC_LOOK;
+    p.row_pitch = tc.np == 16 ? 2048 : 2304;
+    p.n_entries = tc.np == 16 ? 128 : 144;
+    p.nch = (tc.nb + 31) / 32;
+    p.nch0 = (p.nch + 1) / 2;
+    p.btile_bytes = 2 * tc.ksteps * tc.nb * 16;
+    p.tpl = a.tpl;
+    p.sp = a.sp;
+    p.s2p = a.s2p;
+    p.pf = a.pf;
+    p.spitch = a.spitch;
+    p.plane_page_stride = a.plane_page_stride;
+    p.thr_d = a.thr_d;
+    p.sink = a.sink;
+    p.n_pages = n_pages;
+    const int xs = a.r_w - (int)tc.n_w + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
+    if (xs <= 0 || ys <= 0) return cudaSuccess;
+    p.n_xstrips = (xs + 127) / 128;
+    p.n_ysegs = (ys + TC_YSEG - 1) / TC_YSEG;
+    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.row_pitch);
+    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    const int items = n_pages * p.n_xstrips * p.n_ysegs;
+    const int grid = std::min(items, sm_count);
+    // prefilter margin: constants shrunk towards "more candidates" by 2^-12 (>= 500x the fp32 error)
+    const float thr = (float)a.thr_d;
+    const float up = 1.0f + 1.0f / 4096.0f, dn = 1.0f - 1.0f / 4096.0f;
+    const std::vector<float2> &cst = *(const std::vector<float2> *)tc.consts_host;
+    p.dbg_acc = dbg_acc;
+    p.dbg_col = dbg_acc ? dbg_pos % (int)tc.nb : -1;
+    for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
+        if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
+        for (int h = 0; h < 2; h++)
+            for (int j = 0; j < 128; j++) {
+                const int col = (h ? p.nch0 * 32 : 0) + j;
+                float2 c = make_float2(-INFINITY, 0.f);  // padding: d = -inf -> never a candidate
+                if (col < (int)tc.nb) {
+                    const float2 s = cst[(size_t)blk * tc.nb + col];
+                    if (std::isfinite(s.x)) {
+                        const float aa = thr * s.x;  // a = thr * norm_n
+                        c.x = -(aa >= 0 ? aa * dn : aa * up);
+                        c.y = -(s.y * dn);
+                    }
+                }
+                p.cst[h][j] = c;
+            }
+        p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
+        p.tpl_of = tc.tpl_of + (size_t)blk * tc.nb;
+        scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
+    return cudaSuccess;
 }
+
 }  // namespace focr

@@ -15,7 +15,8 @@ struct TcClass {
     uint32_t kchunks = 0;   // 16-byte K chunks per template = n_h * np/16
     uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
     uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]
-    float2 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding/constant templates
+    float2 *consts = nullptr;     // (unused on the device: the constants travel in the kernel parameter bank)
+    void *consts_host = nullptr;  // std::vector<float2>* [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding/constant templates
     uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
 };
 
@@ -28,7 +29,8 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
 void tc_class_release(TcClass &tc);
 bool tc_class_supported(const TcClass &tc);
 void tc_workspace_release(TcWorkspace &ws);
+// dbg_acc/dbg_pos: parity probe -- store the raw numerators of the class's dbg_pos-th template
 cudaError_t launch_scan_tc(TcWorkspace &ws, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
-                           cudaStream_t st, int *n_launches);
+                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc = nullptr, int dbg_pos = -1);
 
 }  // namespace focr
