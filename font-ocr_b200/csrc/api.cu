@@ -77,8 +77,8 @@ struct DevBuf {
 };
 
 struct Slot {  // everything one in-flight chunk of pages needs
-    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, sel, ycut, selcount, flags, out, counts, acc;
-    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow
+    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, cands, sel, ycut, selcount, flags, out, counts, acc;
+    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     uint32_t hits_per_page = 0;
 };
@@ -172,7 +172,7 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slot) {
-        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.sel, &s.ycut,
+        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.cands, &s.sel, &s.ycut,
                           &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
             b->release();
         if (s.flags_host) cudaFreeHost(s.flags_host);
@@ -379,6 +379,9 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     if (any_simt) CU(s.rn.ensure(g.plane_page_stride * nB * 8));
     CU(s.rowcount.ensure(PT * g.r_h * 4));
     CU(s.hits.ensure(hit_cap * sizeof(Hit)));
+    bool any_tc = false;
+    for (auto &ch : b->classes) any_tc |= use_tc(c, ch);
+    if (any_tc) CU(s.cands.ensure(hit_cap * sizeof(Hit)));
     CU(s.sel.ensure(PT * g.sel_cap * 8));
     CU(s.ycut.ensure(PT * 4));
     CU(s.selcount.ensure(PT * 4));
@@ -448,7 +451,12 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.thr_d = (double)threshold;  // ncc.cpp:83
         a.thr_f = threshold;
         a.sink = sink;
+        a.cands = s.cands.as<Hit>();
+        a.cand_cap = sink.hit_cap;
+        a.cand_count = s.flags.as<unsigned int>() + 2;
+        a.cand_max = s.flags.as<unsigned int>() + 3;
         a.acc_out = nullptr;
+        if (tc) CU(cudaMemsetAsync(a.cand_count, 0, 4, st));
         int nl = 0;
         {
             StageTimer tm(c, FOCR_STAGE_SCAN);
@@ -483,7 +491,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         CU(launch_finalize(f, st, &nl));
     }
     c->launches += nl;
-    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 16, cudaMemcpyDeviceToHost, st));
     return FOCR_OK;
 }
 
@@ -491,8 +499,9 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
 static bool chunk_overflowed(focr_ctx *c, Slot &s, uint32_t nB)
 {
     const size_t cap = (size_t)s.hits_per_page * nB;
-    if (s.flags_host[0] > cap) {
-        const size_t need = ((size_t)s.flags_host[0] + nB - 1) / nB;
+    const size_t seen = std::max(s.flags_host[0], s.flags_host[3]);  // hits and prefilter candidates share the capacity
+    if (seen > cap) {
+        const size_t need = (seen + nB - 1) / nB;
         c->hits_per_page = (uint32_t)std::min<size_t>(need + need / 4 + 1024, 0x7FFFFFFFu);
         return true;
     }
@@ -747,6 +756,10 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     a.sink.rowcount = s.rowcount.as<unsigned int>();
     a.sink.T = b->T;
     a.sink.r_h = r_h;
+    a.cands = nullptr;
+    a.cand_cap = 0;
+    a.cand_count = s.flags.as<unsigned int>() + 2;
+    a.cand_max = s.flags.as<unsigned int>() + 3;
     a.acc_out = s.acc.as<uint32_t>();
     int nl = 0;
     if (c->kernel == FOCR_KERNEL_TCGEN05) {

@@ -43,6 +43,10 @@ struct ScanArgs {
     double thr_d;
     float thr_f;
     HitSink sink;
+    // tcgen05 path only: prefilter survivors wait here for the exact f64 pass
+    Hit *cands;
+    uint32_t cand_cap;
+    unsigned int *cand_count, *cand_max;
     uint32_t *acc_out;       // parity probe: raw numerators of ONE template (cls.n_tpl == 1), [y*r_w+x]
 };
 

@@ -19,10 +19,10 @@
 //   exact f64 normalisation (ncc.cpp:212-220) only for the survivors -> warp-aggregated atomic append.
 //   The integer numerators are exact, the decision and the f32 score are bit-identical to the CPU.
 //
-// Warp roles (512 threads, one CTA per SM, persistent over (page, x-strip, y-segment) items):
+// Warp roles (640 threads, one CTA per SM, persistent over (page, x-strip, y-segment) items):
 //   warp 0      TMA producer of raw page rows          warp 1   MMA issuer
 //   warp 2      TMEM allocator                         warp 3   idle
-//   warps 4-7   Toeplitz expansion (thread = window)   warps 8-15  epilogue (two column halves)
+//   warps 4-7   Toeplitz expansion (thread = window)   warps 8-19  epilogue (3 per TMEM lane quarter)
 #include <cooperative_groups.h>
 
 #include <cmath>
@@ -35,7 +35,8 @@ namespace cg = cooperative_groups;
 
 namespace focr {
 
-constexpr int TC_THREADS = 512;
+constexpr int TC_THREADS = 640;      // 4 service + 4 expansion + 12 epilogue warps
+constexpr int TC_EPI_GROUPS = 3;     // epilogue warps per TMEM lane quarter; chunk ch belongs to group ch % 3
 constexpr int TC_RAW_SLOTS = 8;       // raw page-row ring (TMA destination), 160 B each
 constexpr int TC_RAW_BYTES = 160;
 constexpr int TC_LOOK = 6;            // expanded rows the producer side may run ahead of the MMA
@@ -57,23 +58,22 @@ struct TcParams {
     int ring;          // ring slots
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
-    int nch, nch0;     // 32-column chunks in total / handled by epilogue half 0
+    int nch;           // 32-column chunks per accumulator
     const uint8_t *btile;    // [2*ksteps][nb][16]
     uint32_t btile_bytes;
-    const uint32_t *tpl_of;  // [nb] bank index of each column (0xFFFFFFFF = padding)
-    const TplInfo *tpl;
+    uint32_t col_base;       // this launch's first column within the class (N-block * nb)
     const uint32_t *sp;
-    const uint32_t *s2p;
     const float *pf;
     int spitch;
     size_t plane_page_stride;
-    double thr_d;
-    HitSink sink;
+    Hit *cands;                // candidate list (prefilter survivors): {column, y<<16|x, acc bits, page}
+    uint32_t cand_cap;
+    unsigned int *cand_count;
     int n_pages, n_xstrips, n_ysegs;
     uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x] (NULL in production)
     int dbg_col;
-    // prefilter constants per column, negated: {-a', -b'}; half h covers columns (h ? nch0*32 : 0) + j
-    float2 cst[2][128];
+    // prefilter constants per column, negated: {-a', -b'}
+    float2 cst[256];
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -91,11 +91,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done;
+    bool first = true;
     do {
+        // service warps back off between probes so their spinning does not take issue slots from the epilogue
+        if (SLEEP_NS > 0 && !first) __nanosleep(SLEEP_NS);
+        first = false;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -176,46 +181,36 @@ __device__ __forceinline__ bool get_item(const TcParams &p, int idx, Item &it)
     return true;
 }
 
-// the rare path: the reference's exact arithmetic for one prefilter survivor
-__device__ __noinline__ void exact_check(const TcParams &p, uint32_t acc, uint32_t col, uint32_t s_p, size_t plane_off,
-                                         int page, int gx, int y)
+// A prefilter survivor: the raw numerator goes to the candidate list; cand_exact_kernel applies the
+// reference's exact f64 arithmetic afterwards, so the MMA kernel carries no double-precision code.
+__device__ __forceinline__ void push_candidate(const TcParams &p, uint32_t acc, uint32_t col, int page, int gx, int y)
 {
-    const uint32_t t = p.tpl_of[col];
-    if (t == 0xFFFFFFFFu) return;
-    const TplInfo ti = p.tpl[t];
-    const uint32_t s2_p = p.s2p[plane_off];
-    const double rn_p = patch_rnorm(s_p, s2_p, (double)(p.n_w * p.n_h));
-    float sim;
-    if (ncc_exact(acc, s_p, rn_p, ti.s_n, ti.n_recip, ti.rnorm_n, p.thr_d, &sim)) {
-        // warp-aggregated append: one atomic per group of simultaneously hitting lanes
-        auto g = cg::coalesced_threads();
-        unsigned base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(p.sink.hit_count, (unsigned)g.size());
-        base = g.shfl(base, 0);
-        const unsigned slot = base + g.thread_rank();
-        if (slot < p.sink.hit_cap) {
-            Hit h;
-            h.t = t;
-            h.yx = ((uint32_t)y << 16) | (uint32_t)gx;
-            h.sim = sim;
-            h.page = page;
-            p.sink.hits[slot] = h;
-        }
-        atomicAdd(p.sink.rowcount + ((size_t)page * p.sink.T + t) * p.sink.r_h + y, 1u);
+    // warp-aggregated append: one atomic per group of lanes that have a candidate in this column
+    auto g = cg::coalesced_threads();
+    unsigned base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(p.cand_count, (unsigned)g.size());
+    base = g.shfl(base, 0);
+    const unsigned slot = base + g.thread_rank();
+    if (slot < p.cand_cap) {
+        Hit h;
+        h.t = p.col_base + col;  // column within the class; cand_exact_kernel maps it to the bank index
+        h.yx = ((uint32_t)y << 16) | (uint32_t)gx;
+        h.sim = __uint_as_float(acc);
+        h.page = page;
+        p.cands[slot] = h;
     }
 }
 
-// one 32-column chunk of the prefilter: bit (31-j) of the result is the SIGN of
-//   d_j = acc_j - b'_j*S - a'_j*P        (a', b' shrunk by 2^-12: see DESIGN.md "prefilter margin")
-// i.e. a 0 bit marks a candidate.  H selects the constant table so that every constant is a
-// compile-time offset into the kernel parameter bank (no loads in the loop).
-template <int H, int CH>
-__device__ __forceinline__ uint32_t prefilter_chunk(const TcParams &p, const uint32_t (&v)[32], float S, float P)
+// one 32-column chunk of the prefilter: a 0 bit in the result marks a candidate column, where the bit
+// is the SIGN of   d_j = acc_j - b'_j*S - a'_j*P      (a', b' shrunk by 2^-12: DESIGN.md "prefilter margin").
+// Bits: even column j -> bit 31 - j/2, odd column j -> bit 15 - (j-1)/2 (two chains halve the depth).
+__device__ __forceinline__ uint32_t prefilter_chunk(const float2 *__restrict__ cs, const uint32_t (&v)[32], float S,
+                                                    float P)
 {
-    uint32_t m0 = 0, m1 = 0;  // two interleaved chains halve the dependency depth
+    uint32_t m0 = 0, m1 = 0;
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-        const float2 c0 = p.cst[H][CH * 32 + j], c1 = p.cst[H][CH * 32 + j + 1];
+        const float2 c0 = cs[j], c1 = cs[j + 1];
         float d0 = __fmaf_rn(c0.y, S, __int2float_rn((int)v[j]));
         float d1 = __fmaf_rn(c1.y, S, __int2float_rn((int)v[j + 1]));
         d0 = __fmaf_rn(c0.x, P, d0);
@@ -223,39 +218,23 @@ __device__ __forceinline__ uint32_t prefilter_chunk(const TcParams &p, const uin
         m0 = __funnelshift_l(__float_as_uint(d0), m0, 1);
         m1 = __funnelshift_l(__float_as_uint(d1), m1, 1);
     }
-    // interleave back: column j even -> m0 bit (15 - j/2), odd -> m1 bit (15 - j/2); callers only need
-    // "which columns", so return both halves packed: high 16 bits = even columns, low 16 = odd columns
     return (m0 << 16) | (m1 & 0xFFFFu);
 }
 
-template <int H>
-__device__ __forceinline__ void epilogue_row(const TcParams &p, uint32_t tbase, int nchunks, int col0, float S, float P,
-                                             bool valid, uint32_t s_p, size_t plane_off, int page, int gx, int y)
+__device__ __forceinline__ void handle_chunk(const TcParams &p, uint32_t taddr, int col, const uint32_t (&v)[32],
+                                             float S, float P, bool valid, int page, int gx, int y)
 {
-    // tbase already includes the lane quarter and the buffer's first column
-#define FOCR_CHUNK(CH)                                                                                    \
-    if (CH < nchunks) {                                                                                   \
-        uint32_t v[32];                                                                                   \
-        tc_ld32(tbase + col0 + CH * 32, v);                                                               \
-        tc_wait_ld();                                                                                     \
-        uint32_t sign = prefilter_chunk<H, CH>(p, v, S, P);                                               \
-        uint32_t cand = valid ? ~sign : 0u;                                                               \
-        uint32_t any = __reduce_or_sync(0xffffffffu, cand);                                               \
-        while (any) {                                                                                     \
-            const int b = 31 - __clz(any);                                                                \
-            any &= ~(1u << b);                                                                            \
-            /* bit b: b >= 16 -> even column 2*(31-b), else odd column 2*(15-b)+1 */                      \
-            const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;                                      \
-            const uint32_t a = tc_ld1(tbase + col0 + CH * 32 + j);                                        \
-            tc_wait_ld();                                                                                 \
-            if ((cand >> b) & 1u) exact_check(p, a, col0 + CH * 32 + j, s_p, plane_off, page, gx, y);     \
-        }                                                                                                 \
+    const uint32_t sign = prefilter_chunk(p.cst + col, v, S, P);
+    const uint32_t cand = valid ? ~sign : 0u;
+    uint32_t any = __reduce_or_sync(0xffffffffu, cand);
+    while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
+        const int b = 31 - __clz(any);
+        any &= ~(1u << b);
+        const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;
+        const uint32_t a = tc_ld1(taddr + j);  // re-read that column from TMEM (uniform address)
+        tc_wait_ld();
+        if ((cand >> b) & 1u) push_candidate(p, a, col + j, page, gx, y);
     }
-    FOCR_CHUNK(0)
-    FOCR_CHUNK(1)
-    FOCR_CHUNK(2)
-    FOCR_CHUNK(3)
-#undef FOCR_CHUNK
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
@@ -289,7 +268,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, 8);
+            mbar_init(t_empty + i, 4 * TC_EPI_GROUPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -317,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 const int y_end = it.ys1 + p.n_hp - 1;
                 for (int y = it.ys0; y < y_end; y++, g++) {
                     const uint32_t s = g % TC_RAW_SLOTS;
-                    if (g >= TC_RAW_SLOTS) mbar_wait(raw_empty + s, ((g / TC_RAW_SLOTS) - 1) & 1);
+                    if (g >= TC_RAW_SLOTS) mbar_wait<200>(raw_empty + s, ((g / TC_RAW_SLOTS) - 1) & 1);
                     mbar_arrive_expect_tx(raw_full + s, row_bytes);
                     tma_bulk_g2s(raw + s * TC_RAW_BYTES, src + (size_t)y * p.pitch, row_bytes, raw_full + s);
                 }
@@ -343,9 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 for (int j = 0; j < n_out_rows; j++, job++) {
                     // the newest row this output needs (expansion is in order, so older rows are done)
                     const uint32_t gl = g0 + j + p.n_hp - 1;
-                    mbar_wait(a_full + gl % p.ring, (gl / p.ring) & 1);
+                    mbar_wait<32>(a_full + gl % p.ring, (gl / p.ring) & 1);
                     const uint32_t buf = job % p.nbuf;
-                    if (job >= (uint32_t)p.nbuf) mbar_wait(t_empty + buf, ((job / p.nbuf) - 1) & 1);
+                    if (job >= (uint32_t)p.nbuf) mbar_wait<32>(t_empty + buf, ((job / p.nbuf) - 1) & 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * p.nbs;
                     for (int k = 0; k < p.ksteps; k++) {
@@ -379,8 +358,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
             for (int r = 0; r < n_rows; r++, g++) {
                 const uint32_t rs = g % TC_RAW_SLOTS, s = g % p.ring;
-                mbar_wait(raw_full + rs, (g / TC_RAW_SLOTS) & 1);
-                if (g >= (uint32_t)p.ring) mbar_wait(a_empty + s, ((g / p.ring) - 1) & 1);
+                mbar_wait<100>(raw_full + rs, (g / TC_RAW_SLOTS) & 1);
+                if (g >= (uint32_t)p.ring) mbar_wait<100>(a_empty + s, ((g / p.ring) - 1) & 1);
                 const uint32_t *rw = (const uint32_t *)(raw + rs * TC_RAW_BYTES);
                 uint8_t *dst = ring + (size_t)s * p.row_pitch;
                 for (int ee = e; ee < p.n_entries; ee += 128) {
@@ -402,12 +381,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
     } else if (warp >= 8) {
         // ================================================================== epilogue
-        const int q = warp & 3;            // TMEM lane quarter this warp may access
-        const int half = (warp - 8) >> 2;  // column half
-        const int m = q * 32 + lane;       // window within the strip
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int grp = (warp - 8) >> 2;          // chunk ch belongs to group ch % TC_EPI_GROUPS
+        const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int col0 = half ? p.nch0 * 32 : 0;
-        const int nchunks = half ? p.nch - p.nch0 : p.nch0;
         uint32_t job = 0;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
@@ -421,8 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 P = __ldg(p.pf + plane + (size_t)it.ys0 * p.spitch);
             }
             for (int y = it.ys0; y < it.ys1; y++, job++) {
-                // prefetch the next row's window statistics
-                uint32_t s_next = 0;
+                uint32_t s_next = 0;  // prefetch the next row's window statistics
                 float P_next = 0.f;
                 if (x_ok && y + 1 < it.ys1) {
                     s_next = __ldg(p.sp + plane + (size_t)(y + 1) * p.spitch);
@@ -435,12 +411,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 mbar_wait(t_full + buf, (job / p.nbuf) & 1);
                 tc_fence_after();
                 const uint32_t tb = tlane + buf * p.nbs;
-                const size_t plane_off = plane + (size_t)y * p.spitch;
-                if (half == 0)
-                    epilogue_row<0>(p, tb, nchunks, col0, S, Pv, valid, s_p, plane_off, it.page, gx, y);
-                else
-                    epilogue_row<1>(p, tb, nchunks, col0, S, Pv, valid, s_p, plane_off, it.page, gx, y);
-                if (p.dbg_acc && p.dbg_col >= col0 && p.dbg_col < col0 + nchunks * 32) {
+                // software pipeline over this group's chunks: the TMEM load of the next chunk is in
+                // flight while the current one is filtered
+                int ch = grp;
+                if (ch < p.nch) {
+                    uint32_t va[32], vb[32];
+                    tc_ld32(tb + ch * 32, va);
+                    while (true) {
+                        tc_wait_ld();
+                        const int ch1 = ch + TC_EPI_GROUPS;
+                        if (ch1 < p.nch) tc_ld32(tb + ch1 * 32, vb);
+                        handle_chunk(p, tb + ch * 32, ch * 32, va, S, Pv, valid, it.page, gx, y);
+                        if (ch1 >= p.nch) break;
+                        tc_wait_ld();
+                        const int ch2 = ch1 + TC_EPI_GROUPS;
+                        if (ch2 < p.nch) tc_ld32(tb + ch2 * 32, va);
+                        handle_chunk(p, tb + ch1 * 32, ch1 * 32, vb, S, Pv, valid, it.page, gx, y);
+                        if (ch2 >= p.nch) break;
+                        ch = ch2;
+                    }
+                }
+                if (p.dbg_acc && p.dbg_col / 32 % TC_EPI_GROUPS == grp) {
                     const uint32_t a = tc_ld1(tb + p.dbg_col);
                     tc_wait_ld();
                     if (x_ok) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
@@ -460,6 +451,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- exact pass
+// Every prefilter survivor gets the reference's own f64 arithmetic (ncc.cpp:212-220 via ncc_exact,
+// ncc.rs:309-311 via patch_rnorm): the decision `sim > threshold` and the f32 score are bit-identical
+// to the CPU.  Runs right after the MMA launches of a box size, while its statistic planes are live.
+struct CandArgs {
+    const Hit *cands;
+    uint32_t cand_cap;
+    const unsigned int *cand_count;
+    unsigned int *cand_max;  // high-water mark of the candidate count (overflow detection on the host)
+    const uint32_t *tpl_of;  // [n_blocks*nb] bank index per class column (0xFFFFFFFF = padding)
+    const TplInfo *tpl;
+    const uint32_t *sp, *s2p;
+    int spitch;
+    size_t plane_page_stride;
+    double n_d, thr_d;
+    HitSink sink;
+};
+
+__global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
+{
+    const unsigned total = *a.cand_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(a.cand_max, total);
+    const unsigned n = min(total, a.cand_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Hit c = a.cands[i];
+        const uint32_t t = a.tpl_of[c.t];
+        if (t == 0xFFFFFFFFu) continue;
+        const uint32_t y = c.yx >> 16, x = c.yx & 0xFFFFu;
+        const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
+        const uint32_t s_p = a.sp[o], s2_p = a.s2p[o];
+        const TplInfo ti = a.tpl[t];
+        const double rn_p = patch_rnorm(s_p, s2_p, a.n_d);
+        float sim;
+        if (ncc_exact(__float_as_uint(c.sim), s_p, rn_p, ti.s_n, ti.n_recip, ti.rnorm_n, a.thr_d, &sim)) {
+            auto g = cg::coalesced_threads();
+            unsigned base = 0;
+            if (g.thread_rank() == 0) base = atomicAdd(a.sink.hit_count, (unsigned)g.size());
+            base = g.shfl(base, 0);
+            const unsigned slot = base + g.thread_rank();
+            if (slot < a.sink.hit_cap) {
+                Hit h;
+                h.t = t;
+                h.yx = c.yx;
+                h.sim = sim;
+                h.page = c.page;
+                a.sink.hits[slot] = h;
+            }
+            atomicAdd(a.sink.rowcount + ((size_t)c.page * a.sink.T + t) * a.sink.r_h + y, 1u);
+        }
     }
 }
 
@@ -556,16 +599,14 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
     p.n_entries = tc.np == 16 ? 128 : 144;
     p.nch = (tc.nb + 31) / 32;
-    p.nch0 = (p.nch + 1) / 2;
     p.btile_bytes = 2 * tc.ksteps * tc.nb * 16;
-    p.tpl = a.tpl;
     p.sp = a.sp;
-    p.s2p = a.s2p;
     p.pf = a.pf;
     p.spitch = a.spitch;
     p.plane_page_stride = a.plane_page_stride;
-    p.thr_d = a.thr_d;
-    p.sink = a.sink;
+    p.cands = a.cands;
+    p.cand_cap = a.cand_cap;
+    p.cand_count = a.cand_count;
     p.n_pages = n_pages;
     const int xs = a.r_w - (int)tc.n_w + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
     if (xs <= 0 || ys <= 0) return cudaSuccess;
@@ -584,23 +625,41 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.dbg_col = dbg_acc ? dbg_pos % (int)tc.nb : -1;
     for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
-        for (int h = 0; h < 2; h++)
-            for (int j = 0; j < 128; j++) {
-                const int col = (h ? p.nch0 * 32 : 0) + j;
-                float2 c = make_float2(-INFINITY, 0.f);  // padding: d = -inf -> never a candidate
-                if (col < (int)tc.nb) {
-                    const float2 s = cst[(size_t)blk * tc.nb + col];
-                    if (std::isfinite(s.x)) {
-                        const float aa = thr * s.x;  // a = thr * norm_n
-                        c.x = -(aa >= 0 ? aa * dn : aa * up);
-                        c.y = -(s.y * dn);
-                    }
+        for (int col = 0; col < 256; col++) {
+            float2 c = make_float2(-INFINITY, 0.f);  // padding: d = -inf -> never a candidate
+            if (col < (int)tc.nb) {
+                const float2 s = cst[(size_t)blk * tc.nb + col];
+                if (std::isfinite(s.x)) {
+                    const float aa = thr * s.x;  // a = thr * norm_n
+                    c.x = -(aa >= 0 ? aa * dn : aa * up);
+                    c.y = -(s.y * dn);
                 }
-                p.cst[h][j] = c;
             }
+            p.cst[col] = c;
+        }
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
-        p.tpl_of = tc.tpl_of + (size_t)blk * tc.nb;
+        p.col_base = blk * tc.nb;
         scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_launches) (*n_launches)++;
+    }
+    if (!dbg_acc) {
+        CandArgs ca;
+        ca.cands = a.cands;
+        ca.cand_cap = a.cand_cap;
+        ca.cand_count = a.cand_count;
+        ca.cand_max = a.cand_max;
+        ca.tpl_of = tc.tpl_of;
+        ca.tpl = a.tpl;
+        ca.sp = a.sp;
+        ca.s2p = a.s2p;
+        ca.spitch = a.spitch;
+        ca.plane_page_stride = a.plane_page_stride;
+        ca.n_d = (double)(tc.n_w * tc.n_h);
+        ca.thr_d = a.thr_d;
+        ca.sink = a.sink;
+        cand_exact_kernel<<<sm_count * 4, 256, 0, st>>>(ca);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
