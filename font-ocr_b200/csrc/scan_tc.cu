@@ -52,13 +52,15 @@ struct TcParams {
     int n_w, n_h, np;
     int n_hp;          // page rows an output row needs (n_h rounded up to 2 when np == 16)
     int ksteps;        // tcgen05.mma per output row
-    int nb;            // N of the MMA (templates per launch, multiple of 16)
-    int nbs;           // TMEM column stride between accumulator buffers (nb rounded up to 32)
+    int nb;            // templates per launch (multiple of 16; the B tile in shared memory)
+    int nsub;          // the N dimension is issued as nsub MMAs of n_mma columns each (finer TMEM buffering)
+    int n_mma;         // N of one tcgen05.mma (multiple of 16, <= 128 when nsub > 1)
+    int nunits;        // 16-column epilogue units per accumulator buffer (n_mma / 16)
+    int nbs;           // TMEM column stride between accumulator buffers (n_mma rounded up to 32)
     int nbuf;          // accumulator buffers
     int ring;          // ring slots
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
-    int nch;           // 32-column chunks per accumulator
     const uint8_t *btile;    // [2*ksteps][nb][16]
     uint32_t btile_bytes;
     uint32_t col_base;       // this launch's first column within the class (N-block * nb)
@@ -92,9 +94,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 template <int SLEEP_NS = 0>
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity)
 {
-    const uint32_t addr = smem_u32(bar);
     uint32_t done;
     bool first = true;
     do {
@@ -109,6 +110,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "r"(addr), "r"(parity)
             : "memory");
     } while (!done);
+}
+template <int SLEEP_NS = 0>
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    mbar_wait_addr<SLEEP_NS>(smem_u32(bar), parity);
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -125,6 +131,10 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_addr)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate)
@@ -155,6 +165,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// packed fp32x2 FMA (sm_100 FFMA2): two columns per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
 }
 __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
 {
@@ -201,31 +234,34 @@ __device__ __forceinline__ void push_candidate(const TcParams &p, uint32_t acc, 
     }
 }
 
-// one 32-column chunk of the prefilter: a 0 bit in the result marks a candidate column, where the bit
+// one 16-column unit of the prefilter: a 0 bit in the result marks a candidate column, where the bit
 // is the SIGN of   d_j = acc_j - b'_j*S - a'_j*P      (a', b' shrunk by 2^-12: DESIGN.md "prefilter margin").
-// Bits: even column j -> bit 31 - j/2, odd column j -> bit 15 - (j-1)/2 (two chains halve the depth).
-__device__ __forceinline__ uint32_t prefilter_chunk(const float2 *__restrict__ cs, const uint32_t (&v)[32], float S,
-                                                    float P)
+// cs[i] = {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}: one LDS.128 (broadcast) and two FFMA2 per column pair.
+// Bits: even column j -> bit 15 - j/2 of the high half-word, odd column j -> bit 15 - (j-1)/2 of the low one.
+__device__ __forceinline__ uint32_t prefilter_unit(const float4 *__restrict__ cs, const uint32_t (&v)[16],
+                                                   unsigned long long SS, unsigned long long PP)
 {
     uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-        const float2 c0 = cs[j], c1 = cs[j + 1];
-        float d0 = __fmaf_rn(c0.y, S, __int2float_rn((int)v[j]));
-        float d1 = __fmaf_rn(c1.y, S, __int2float_rn((int)v[j + 1]));
-        d0 = __fmaf_rn(c0.x, P, d0);
-        d1 = __fmaf_rn(c1.x, P, d1);
-        m0 = __funnelshift_l(__float_as_uint(d0), m0, 1);
-        m1 = __funnelshift_l(__float_as_uint(d1), m1, 1);
+    for (int j = 0; j < 16; j += 2) {
+        const float4 c = cs[j >> 1];
+        unsigned long long d = pack2(__int2float_rn((int)v[j]), __int2float_rn((int)v[j + 1]));
+        d = ffma2(pack2(c.x, c.y), SS, d);
+        d = ffma2(pack2(c.z, c.w), PP, d);
+        uint32_t d0, d1;
+        asm("mov.b64 {%0,%1}, %2;" : "=r"(d0), "=r"(d1) : "l"(d));
+        m0 = __funnelshift_l(d0, m0, 1);
+        m1 = __funnelshift_l(d1, m1, 1);
     }
-    return (m0 << 16) | (m1 & 0xFFFFu);
+    return (m0 << 24) | ((m1 & 0xFFu) << 8);  // even columns in bits 31..24, odd columns in bits 15..8
 }
 
-__device__ __forceinline__ void handle_chunk(const TcParams &p, uint32_t taddr, int col, const uint32_t (&v)[32],
-                                             float S, float P, bool valid, int page, int gx, int y)
+__device__ __forceinline__ void handle_unit(const TcParams &p, const float4 *cst_s, uint32_t taddr, int col,
+                                            const uint32_t (&v)[16], unsigned long long SS, unsigned long long PP,
+                                            bool valid, int page, int gx, int y)
 {
-    const uint32_t sign = prefilter_chunk(p.cst + col, v, S, P);
-    const uint32_t cand = valid ? ~sign : 0u;
+    const uint32_t sign = prefilter_unit(cst_s + (col >> 1), v, SS, PP);
+    const uint32_t cand = valid ? (~sign & 0xFF00FF00u) : 0u;
     uint32_t any = __reduce_or_sync(0xffffffffu, cand);
     while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
         const int b = 31 - __clz(any);
@@ -253,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint64_t *t_full = a_empty + TC_RING_MAX;         // TC_MAX_BUF
     uint64_t *t_empty = t_full + TC_MAX_BUF;          // TC_MAX_BUF
     uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
+    float4 *cst_s = (float4 *)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // 128 x {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -272,6 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x >= 128 && threadIdx.x < 256) {
+        const int i = threadIdx.x - 128;
+        cst_s[i] = make_float4(p.cst[2 * i].y, p.cst[2 * i + 1].y, p.cst[2 * i].x, p.cst[2 * i + 1].x);
+    }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                      "r"(512)
@@ -289,77 +330,96 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             mbar_arrive_expect_tx(bar_btile, p.btile_bytes);
             tma_bulk_g2s(btile, p.btile, p.btile_bytes, bar_btile);
             const uint32_t row_bytes = 128 + p.np;
-            uint32_t g = 0;  // raw rows produced so far
+            uint32_t rs = 0, rpar = 1;  // raw slot and the parity of its PREVIOUS use (nothing to wait for in round 0)
+            bool first_round = true;
             Item it;
             for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
-                const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0;
-                const int y_end = it.ys1 + p.n_hp - 1;
-                for (int y = it.ys0; y < y_end; y++, g++) {
-                    const uint32_t s = g % TC_RAW_SLOTS;
-                    if (g >= TC_RAW_SLOTS) mbar_wait<200>(raw_empty + s, ((g / TC_RAW_SLOTS) - 1) & 1);
-                    mbar_arrive_expect_tx(raw_full + s, row_bytes);
-                    tma_bulk_g2s(raw + s * TC_RAW_BYTES, src + (size_t)y * p.pitch, row_bytes, raw_full + s);
+                const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0 + (size_t)it.ys0 * p.pitch;
+                const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
+                for (int r = 0; r < n_rows; r++, src += p.pitch) {
+                    if (!first_round) mbar_wait<200>(raw_empty + rs, rpar);
+                    mbar_arrive_expect_tx(raw_full + rs, row_bytes);
+                    tma_bulk_g2s(raw + rs * TC_RAW_BYTES, src, row_bytes, raw_full + rs);
+                    if (++rs == TC_RAW_SLOTS) {
+                        rs = 0;
+                        rpar ^= 1;
+                        first_round = false;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
+        // Everything in this loop is incremental (no division, no 64-bit descriptor rebuild): a single
+        // thread issues all tensor work of the SM, so its instruction count per output row is what
+        // bounds the kernel once the epilogue keeps up.
         if (lane == 0) {
             const uint32_t idesc = (2u << 4)                      // D format: S32
                                    | (0u << 7) | (0u << 10)       // A, B: unsigned 8-bit
                                    | (0u << 15) | (0u << 16)      // A, B: K-major
-                                   | ((uint32_t)(p.nb >> 3) << 17)  // N
+                                   | ((uint32_t)(p.n_mma >> 3) << 17)  // N
                                    | ((128u >> 4) << 24);         // M = 128
-            const uint32_t b_lbo = (uint32_t)p.nb * 16u;
-            const uint32_t a_lbo = p.np == 16 ? (uint32_t)p.row_pitch : 256u;
-            const uint32_t ring_addr = smem_u32(ring), btile_addr = smem_u32(btile);
+            const uint32_t ring_n = p.ring, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nsub = p.nsub;
+            const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4;
+            const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
+            const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
+            const uint32_t a_step = p.np == 16 ? 2u : 1u;          // ring slots consumed per K step
+            const uint32_t desc_hi = (128u >> 4) | (1u << 14);     // SBO = 128 B, version = 1
+            const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
+            const uint32_t b_lo0 = ((smem_u32(btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+            const uint32_t bars_a_full = smem_u32(a_full), bars_a_empty = smem_u32(a_empty);
             mbar_wait(bar_btile, 0);
-            uint32_t g0 = 0;  // expanded-row index of the current item's first row
-            uint32_t job = 0;  // output rows issued so far (accumulator buffer sequence)
+            uint32_t s_first = 0;                 // ring slot of the output row's first page row
+            uint32_t s_new = n_hp - 1, par_new = 0;  // slot/parity of the newest page row the output needs
+            while (s_new >= ring_n) s_new -= ring_n, par_new ^= 1;
+            uint32_t buf = 0, bpar = 0;
+            bool first_round = true;
             Item it;
             for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
                 const int n_out_rows = it.ys1 - it.ys0;
-                for (int j = 0; j < n_out_rows; j++, job++) {
-                    // the newest row this output needs (expansion is in order, so older rows are done)
-                    const uint32_t gl = g0 + j + p.n_hp - 1;
-                    mbar_wait<32>(a_full + gl % p.ring, (gl / p.ring) & 1);
-                    const uint32_t buf = job % p.nbuf;
-                    if (job >= (uint32_t)p.nbuf) mbar_wait<32>(t_empty + buf, ((job / p.nbuf) - 1) & 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * p.nbs;
-                    for (int k = 0; k < p.ksteps; k++) {
-                        uint32_t a_addr;
-                        if (p.np == 16) {
-                            const uint32_t s = (g0 + j + 2 * k) % p.ring;  // pair (s, s+1); slot `ring` mirrors slot 0
-                            a_addr = ring_addr + s * p.row_pitch;
-                        } else {
-                            const uint32_t s = (g0 + j + k) % p.ring;      // chunks 0 and 1 of one row, 16 windows apart
-                            a_addr = ring_addr + s * p.row_pitch;
+                for (int j = 0; j < n_out_rows; j++) {
+                    mbar_wait_addr<20>(bars_a_full + s_new * 8, par_new);
+                    for (uint32_t sub = 0; sub < nsub; sub++) {
+                        if (!first_round) mbar_wait<20>(t_empty + buf, bpar ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + buf * p.nbs;
+                        uint32_t s = s_first, b_lo = b_lo0 + sub * (uint32_t)p.n_mma;  // template n sits n*16 B into a K chunk
+                        for (uint32_t k = 0; k < ksteps; k++) {
+                            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo0 + s * pitch16);
+                            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
+                            tc_mma_i8(d_tmem, adesc, bdesc, idesc, k);
+                            s += a_step;
+                            if (s >= ring_n) s -= ring_n;
+                            b_lo += 2 * b_lbo16;
                         }
-                        const uint64_t adesc = make_desc(a_addr, a_lbo, 128);
-                        const uint64_t bdesc = make_desc(btile_addr + (uint32_t)(2 * k) * b_lbo, b_lbo, 128);
-                        tc_mma_i8(d_tmem, adesc, bdesc, idesc, k > 0);
+                        tc_commit(t_full + buf);                     // accumulator ready for the epilogue
+                        if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
                     }
-                    tc_commit(t_full + buf);                       // accumulator ready for the epilogue
-                    tc_commit(a_empty + (g0 + j) % p.ring);        // row g0+j is not needed by later outputs
+                    tc_commit_addr(bars_a_empty + s_first * 8);      // row s_first is not needed by later outputs
+                    if (++s_first == ring_n) s_first = 0;
+                    if (++s_new == ring_n) s_new = 0, par_new ^= 1;
                 }
                 // the last n_hp-1 rows of the item are never the first row of an output: release them too
-                for (int j = n_out_rows; j < n_out_rows + p.n_hp - 1; j++) tc_commit(a_empty + (g0 + j) % p.ring);
-                g0 += n_out_rows + p.n_hp - 1;
+                for (uint32_t r = 0; r + 1 < n_hp; r++) {
+                    tc_commit_addr(bars_a_empty + s_first * 8);
+                    if (++s_first == ring_n) s_first = 0;
+                    if (++s_new == ring_n) s_new = 0, par_new ^= 1;
+                }
             }
         }
     } else if (warp >= 4 && warp < 8) {
         // ================================================================== Toeplitz expansion
         const int e = threadIdx.x - 128;  // window index 0..127
         const bool mirror = p.np == 16;
-        uint32_t g = 0;
+        const uint32_t ring_n = p.ring;
+        uint32_t rs = 0, rpar = 0, s = 0, spar = 1;
+        bool first_round = true;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
-            for (int r = 0; r < n_rows; r++, g++) {
-                const uint32_t rs = g % TC_RAW_SLOTS, s = g % p.ring;
-                mbar_wait<100>(raw_full + rs, (g / TC_RAW_SLOTS) & 1);
-                if (g >= (uint32_t)p.ring) mbar_wait<100>(a_empty + s, ((g / p.ring) - 1) & 1);
+            for (int r = 0; r < n_rows; r++) {
+                mbar_wait<100>(raw_full + rs, rpar);
+                if (!first_round) mbar_wait<100>(a_empty + s, spar);
                 const uint32_t *rw = (const uint32_t *)(raw + rs * TC_RAW_BYTES);
                 uint8_t *dst = ring + (size_t)s * p.row_pitch;
                 for (int ee = e; ee < p.n_entries; ee += 128) {
@@ -372,11 +432,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     o.z = __funnelshift_r(w2, w3, sh);
                     o.w = __funnelshift_r(w3, w4, sh);
                     *(uint4 *)(dst + ee * 16) = o;
-                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)p.ring * p.row_pitch + ee * 16) = o;
+                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)ring_n * p.row_pitch + ee * 16) = o;
                 }
                 fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
                 mbar_arrive(a_full + s);
                 mbar_arrive(raw_empty + rs);
+                if (++rs == TC_RAW_SLOTS) rs = 0, rpar ^= 1;
+                if (++s == ring_n) s = 0, spar ^= 1, first_round = false;
             }
         }
     } else if (warp >= 8) {
@@ -385,7 +447,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const int grp = (warp - 8) >> 2;          // chunk ch belongs to group ch % TC_EPI_GROUPS
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t job = 0;
+        const uint32_t nbuf = p.nbuf;
+        const int nunits = p.nunits, urot = p.nunits % TC_EPI_GROUPS;
+        int ufirst = grp;  // first unit of the current buffer that belongs to this group
+        uint32_t buf = 0, bpar = 0;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int gx = it.x0 + m;
@@ -397,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 s_p = __ldg(p.sp + plane + (size_t)it.ys0 * p.spitch);
                 P = __ldg(p.pf + plane + (size_t)it.ys0 * p.spitch);
             }
-            for (int y = it.ys0; y < it.ys1; y++, job++) {
+            for (int y = it.ys0; y < it.ys1; y++) {
                 uint32_t s_next = 0;  // prefetch the next row's window statistics
                 float P_next = 0.f;
                 if (x_ok && y + 1 < it.ys1) {
@@ -407,38 +472,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 const bool valid = x_ok && P < __int_as_float(0x7f800000);  // +inf marks a constant window
                 const float S = (float)s_p;
                 const float Pv = valid ? P : 0.f;
-                const uint32_t buf = job % p.nbuf;
-                mbar_wait(t_full + buf, (job / p.nbuf) & 1);
-                tc_fence_after();
-                const uint32_t tb = tlane + buf * p.nbs;
-                // software pipeline over this group's chunks: the TMEM load of the next chunk is in
-                // flight while the current one is filtered
-                int ch = grp;
-                if (ch < p.nch) {
-                    uint32_t va[32], vb[32];
-                    tc_ld32(tb + ch * 32, va);
-                    while (true) {
-                        tc_wait_ld();
-                        const int ch1 = ch + TC_EPI_GROUPS;
-                        if (ch1 < p.nch) tc_ld32(tb + ch1 * 32, vb);
-                        handle_chunk(p, tb + ch * 32, ch * 32, va, S, Pv, valid, it.page, gx, y);
-                        if (ch1 >= p.nch) break;
-                        tc_wait_ld();
-                        const int ch2 = ch1 + TC_EPI_GROUPS;
-                        if (ch2 < p.nch) tc_ld32(tb + ch2 * 32, va);
-                        handle_chunk(p, tb + ch1 * 32, ch1 * 32, vb, S, Pv, valid, it.page, gx, y);
-                        if (ch2 >= p.nch) break;
-                        ch = ch2;
+                const unsigned long long SS = pack2(S, S), PP = pack2(Pv, Pv);
+                for (int sub = 0; sub < p.nsub; sub++) {
+                    mbar_wait(t_full + buf, bpar);
+                    tc_fence_after();
+                    const uint32_t tb = tlane + buf * p.nbs;
+                    const int cbase = sub * p.n_mma;
+                    // this group's 16-column units of the buffer, software pipelined: the TMEM load of
+                    // the next unit is in flight while the current one is filtered
+                    int u = ufirst;
+                    if (u < nunits) {
+                        uint32_t va[16], vb[16];
+                        tc_ld16(tb + u * 16, va);
+                        while (true) {
+                            tc_wait_ld();
+                            const int u1 = u + TC_EPI_GROUPS;
+                            if (u1 < nunits) tc_ld16(tb + u1 * 16, vb);
+                            handle_unit(p, cst_s, tb + u * 16, cbase + u * 16, va, SS, PP, valid, it.page, gx, y);
+                            if (u1 >= nunits) break;
+                            tc_wait_ld();
+                            const int u2 = u1 + TC_EPI_GROUPS;
+                            if (u2 < nunits) tc_ld16(tb + u2 * 16, va);
+                            handle_unit(p, cst_s, tb + u1 * 16, cbase + u1 * 16, vb, SS, PP, valid, it.page, gx, y);
+                            if (u2 >= nunits) break;
+                            u = u2;
+                        }
                     }
+                    if (p.dbg_acc && p.dbg_col >= cbase && p.dbg_col < cbase + p.n_mma && grp == 0) {
+                        const uint32_t a = tc_ld1(tb + p.dbg_col - cbase);
+                        tc_wait_ld();
+                        if (x_ok) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + buf);
+                    if (++buf == nbuf) buf = 0, bpar ^= 1;
+                    // round-robin the units over the groups ACROSS buffers so the groups stay balanced
+                    ufirst -= urot;
+                    if (ufirst < 0) ufirst += TC_EPI_GROUPS;
                 }
-                if (p.dbg_acc && p.dbg_col / 32 % TC_EPI_GROUPS == grp) {
-                    const uint32_t a = tc_ld1(tb + p.dbg_col);
-                    tc_wait_ld();
-                    if (x_ok) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + buf);
                 s_p = s_next;
                 P = P_next;
             }
@@ -510,7 +582,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int row_pitch)
 {
     return ((btile_bytes + 127) & ~127u) + (size_t)(ring + 1) * row_pitch + TC_RAW_SLOTS * TC_RAW_BYTES +
-           (1 + 2 * TC_RAW_SLOTS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 16;
+           (1 + 2 * TC_RAW_SLOTS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 64 + 128 * 16;
 }
 
 int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
@@ -533,6 +605,7 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     if (nb_max < 16) return 0;
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
     tc.nb = ((n_tpl + tc.n_blocks - 1) / tc.n_blocks + 15) & ~15u;
+    if (tc.nb > 128) tc.nb = (tc.nb + 31) & ~31u;  // issued as two MMAs of nb/2 (a multiple of 16) columns
     const size_t tile = (size_t)2 * tc.ksteps * tc.nb * 16;
     std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
     std::vector<float2> cst((size_t)tc.n_blocks * tc.nb);
@@ -593,12 +666,14 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
     p.ksteps = tc.ksteps;
     p.nb = tc.nb;
-    p.nbs = (tc.nb + 31) & ~31;
+    p.nsub = tc.nb > 128 ? 2 : 1;           // tc_class_build makes nb a multiple of 32 when it exceeds 128
+    p.n_mma = tc.nb / p.nsub;
+    p.nunits = p.n_mma / 16;
+    p.nbs = (p.n_mma + 31) & ~31;
     p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
     p.ring = p.n_hp + TC_LOOK;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
     p.n_entries = tc.np == 16 ? 128 : 144;
-    p.nch = (tc.nb + 31) / 32;
     p.btile_bytes = 2 * tc.ksteps * tc.nb * 16;
     p.sp = a.sp;
     p.pf = a.pf;
