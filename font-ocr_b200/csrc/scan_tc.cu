@@ -19,13 +19,14 @@
 //   exact f64 normalisation (ncc.cpp:212-220) only for the survivors -> warp-aggregated atomic append.
 //   The integer numerators are exact, the decision and the f32 score are bit-identical to the CPU.
 //
-// Warp roles (640 threads, one CTA per SM, persistent over (page, x-strip, y-segment) items):
+// Warp roles (768 threads, one CTA per SM, persistent over (page, x-strip, y-segment) items):
 //   warp 0      TMA producer of raw page rows          warp 1   MMA issuer
 //   warp 2      TMEM allocator                         warp 3   idle
-//   warps 4-7   Toeplitz expansion (thread = window)   warps 8-19  epilogue (3 per TMEM lane quarter)
+//   warps 4-7   Toeplitz expansion (thread = window)   warps 8-23  epilogue (4 per TMEM lane quarter)
 #include <cooperative_groups.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,12 +36,14 @@ namespace cg = cooperative_groups;
 
 namespace focr {
 
-constexpr int TC_THREADS = 640;      // 4 service + 4 expansion + 12 epilogue warps
-constexpr int TC_EPI_GROUPS = 3;     // epilogue warps per TMEM lane quarter; chunk ch belongs to group ch % 3
-constexpr int TC_RAW_SLOTS = 8;       // raw page-row ring (TMA destination), 160 B each
+constexpr int TC_THREADS = 768;      // 4 service + 4 expansion + 16 epilogue warps
+constexpr int TC_EPI_GROUPS = 4;     // epilogue warps per TMEM lane quarter (= per SM sub-partition)
+constexpr int TC_G = 4;               // page rows per pipeline group: one mbarrier handshake per 4 rows
+constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
+constexpr int TC_RAW_SLOTS = TC_RAW_GROUPS * TC_G;
 constexpr int TC_RAW_BYTES = 160;
-constexpr int TC_LOOK = 6;            // expanded rows the producer side may run ahead of the MMA
-constexpr int TC_RING_MAX = 40;       // max ring slots (n_hp + TC_LOOK)
+constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side may run ahead of the MMA
+constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
 constexpr int TC_YSEG = 128;          // output rows per work item
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
@@ -55,10 +58,11 @@ struct TcParams {
     int nb;            // templates per launch (multiple of 16; the B tile in shared memory)
     int nsub;          // the N dimension is issued as nsub MMAs of n_mma columns each (finer TMEM buffering)
     int n_mma;         // N of one tcgen05.mma (multiple of 16, <= 128 when nsub > 1)
-    int nunits;        // 16-column epilogue units per accumulator buffer (n_mma / 16)
+    int nunits;        // 32-column epilogue units per accumulator buffer
     int nbs;           // TMEM column stride between accumulator buffers (n_mma rounded up to 32)
     int nbuf;          // accumulator buffers
-    int ring;          // ring slots
+    int ring;          // ring slots (rows) = ring_groups * 4
+    int ring_groups;
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
     const uint8_t *btile;    // [2*ksteps][nb][16]
@@ -72,6 +76,7 @@ struct TcParams {
     uint32_t cand_cap;
     unsigned int *cand_count;
     int n_pages, n_xstrips, n_ysegs;
+    int dbg_mode;       // timing experiments only (env FOCR_TC_DBG): 1 = epilogue skips the TMEM reads, 2 = reads but no filter
     uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x] (NULL in production)
     int dbg_col;
     // prefilter constants per column, negated: {-a', -b'}
@@ -92,6 +97,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity)
@@ -163,8 +182,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
+        : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
@@ -173,8 +191,35 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
+        : "r"(taddr));
+}
+// tcgen05.wait::ld that is ordered against the USES of v through register dependencies instead of a
+// memory clobber, so that independent shared-memory loads (the prefilter constants) can be hoisted above it
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+__device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+__device__ __forceinline__ uint32_t ldg_now_u32(const uint32_t *p)
+{
+    uint32_t v;  // volatile: issue the load HERE (the compiler would otherwise sink a prefetch to its use)
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_now_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 // packed fp32x2 FMA (sm_100 FFMA2): two columns per instruction
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi)
@@ -234,16 +279,16 @@ __device__ __forceinline__ void push_candidate(const TcParams &p, uint32_t acc, 
     }
 }
 
-// one 16-column unit of the prefilter: a 0 bit in the result marks a candidate column, where the bit
+// one 32-column unit of the prefilter: a 0 bit in the result marks a candidate column, where the bit
 // is the SIGN of   d_j = acc_j - b'_j*S - a'_j*P      (a', b' shrunk by 2^-12: DESIGN.md "prefilter margin").
 // cs[i] = {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}: one LDS.128 (broadcast) and two FFMA2 per column pair.
-// Bits: even column j -> bit 15 - j/2 of the high half-word, odd column j -> bit 15 - (j-1)/2 of the low one.
-__device__ __forceinline__ uint32_t prefilter_unit(const float4 *__restrict__ cs, const uint32_t (&v)[16],
+// Bits: even column j -> bit 31 - j/2, odd column j -> bit 15 - (j-1)/2.
+__device__ __forceinline__ uint32_t prefilter_unit(const float4 *__restrict__ cs, const uint32_t (&v)[32],
                                                    unsigned long long SS, unsigned long long PP)
 {
     uint32_t m0 = 0, m1 = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
+    for (int j = 0; j < 32; j += 2) {
         const float4 c = cs[j >> 1];
         unsigned long long d = pack2(__int2float_rn((int)v[j]), __int2float_rn((int)v[j + 1]));
         d = ffma2(pack2(c.x, c.y), SS, d);
@@ -253,23 +298,25 @@ __device__ __forceinline__ uint32_t prefilter_unit(const float4 *__restrict__ cs
         m0 = __funnelshift_l(d0, m0, 1);
         m1 = __funnelshift_l(d1, m1, 1);
     }
-    return (m0 << 24) | ((m1 & 0xFFu) << 8);  // even columns in bits 31..24, odd columns in bits 15..8
+    return __byte_perm(m1, m0, 0x5410);  // (m0 << 16) | (m1 & 0xFFFF) in one PRMT
 }
 
 __device__ __forceinline__ void handle_unit(const TcParams &p, const float4 *cst_s, uint32_t taddr, int col,
-                                            const uint32_t (&v)[16], unsigned long long SS, unsigned long long PP,
+                                            const uint32_t (&v)[32], unsigned long long SS, unsigned long long PP,
                                             bool valid, int page, int gx, int y)
 {
     const uint32_t sign = prefilter_unit(cst_s + (col >> 1), v, SS, PP);
-    const uint32_t cand = valid ? (~sign & 0xFF00FF00u) : 0u;
-    uint32_t any = __reduce_or_sync(0xffffffffu, cand);
-    while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
-        const int b = 31 - __clz(any);
-        any &= ~(1u << b);
-        const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;
-        const uint32_t a = tc_ld1(taddr + j);  // re-read that column from TMEM (uniform address)
-        tc_wait_ld();
-        if ((cand >> b) & 1u) push_candidate(p, a, col + j, page, gx, y);
+    const uint32_t cand = valid ? ~sign : 0u;
+    if (__any_sync(0xffffffffu, cand != 0)) {
+        uint32_t any = __reduce_or_sync(0xffffffffu, cand);
+        while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
+            const int b = 31 - __clz(any);
+            any &= ~(1u << b);
+            const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;
+            const uint32_t a = tc_ld1(taddr + j);  // re-read that column from TMEM (uniform address)
+            tc_wait_ld();
+            if ((cand >> b) & 1u) push_candidate(p, a, col + j, page, gx, y);
+        }
     }
 }
 
@@ -282,26 +329,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint8_t *raw = ring + (size_t)(p.ring + 1) * p.row_pitch;  // +1: mirror of slot 0 for (ring-1, 0) pairs
     uint64_t *bars = (uint64_t *)(raw + TC_RAW_SLOTS * TC_RAW_BYTES);
     uint64_t *bar_btile = bars;                       // 1
-    uint64_t *raw_full = bars + 1;                    // TC_RAW_SLOTS
-    uint64_t *raw_empty = raw_full + TC_RAW_SLOTS;    // TC_RAW_SLOTS
-    uint64_t *a_full = raw_empty + TC_RAW_SLOTS;      // TC_RING_MAX
+    uint64_t *raw_full = bars + 1;                    // TC_RAW_GROUPS
+    uint64_t *raw_empty = raw_full + TC_RAW_GROUPS;   // TC_RAW_GROUPS
+    uint64_t *a_full = raw_empty + TC_RAW_GROUPS;     // TC_RING_MAX
     uint64_t *a_empty = a_full + TC_RING_MAX;         // TC_RING_MAX
     uint64_t *t_full = a_empty + TC_RING_MAX;         // TC_MAX_BUF
     uint64_t *t_empty = t_full + TC_MAX_BUF;          // TC_MAX_BUF
     uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
-    float4 *cst_s = (float4 *)(((uintptr_t)(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // 128 x {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}
+    // 128 x {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}; offset arithmetic on `smem` keeps it a shared-space pointer (LDS.128)
+    float4 *cst_s = (float4 *)(smem + (((size_t)((uint8_t *)(tmem_ptr + 4) - smem) + 15) & ~(size_t)15));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_btile, 1);
-        for (int i = 0; i < TC_RAW_SLOTS; i++) {
+        for (int i = 0; i < TC_RAW_GROUPS; i++) {
             mbar_init(raw_full + i, 1);
-            mbar_init(raw_empty + i, 128);
+            mbar_init(raw_empty + i, 4);   // one arrival per expansion warp
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
-            mbar_init(a_full + i, 128);
-            mbar_init(a_empty + i, 1);
+            mbar_init(a_full + i, 4);
+            mbar_init(a_empty + i, 1);     // tcgen05.commit
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
@@ -324,132 +372,190 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // rows this CTA will stream through the pipeline (all its items); the expansion warps need nothing else
+    uint32_t total_rows = 0;
+    if (warp < 8) {
+        Item it;
+        for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) total_rows += (it.ys1 - it.ys0) + p.n_hp - 1;
+    }
+
     if (warp == 0) {
-        // ================================================================== TMA producer
-        if (lane == 0) {
+        // ================================================================== TMA producer (warp-uniform, one elected lane issues)
+        if (elect_one()) {
             mbar_arrive_expect_tx(bar_btile, p.btile_bytes);
             tma_bulk_g2s(btile, p.btile, p.btile_bytes, bar_btile);
-            const uint32_t row_bytes = 128 + p.np;
-            uint32_t rs = 0, rpar = 1;  // raw slot and the parity of its PREVIOUS use (nothing to wait for in round 0)
-            bool first_round = true;
-            Item it;
-            for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
-                const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0 + (size_t)it.ys0 * p.pitch;
-                const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
-                for (int r = 0; r < n_rows; r++, src += p.pitch) {
-                    if (!first_round) mbar_wait<200>(raw_empty + rs, rpar);
-                    mbar_arrive_expect_tx(raw_full + rs, row_bytes);
-                    tma_bulk_g2s(raw + rs * TC_RAW_BYTES, src, row_bytes, raw_full + rs);
-                    if (++rs == TC_RAW_SLOTS) {
-                        rs = 0;
-                        rpar ^= 1;
-                        first_round = false;
-                    }
-                }
-            }
         }
-    } else if (warp == 1) {
-        // ================================================================== MMA issuer
-        // Everything in this loop is incremental (no division, no 64-bit descriptor rebuild): a single
-        // thread issues all tensor work of the SM, so its instruction count per output row is what
-        // bounds the kernel once the epilogue keeps up.
-        if (lane == 0) {
-            const uint32_t idesc = (2u << 4)                      // D format: S32
-                                   | (0u << 7) | (0u << 10)       // A, B: unsigned 8-bit
-                                   | (0u << 15) | (0u << 16)      // A, B: K-major
-                                   | ((uint32_t)(p.n_mma >> 3) << 17)  // N
-                                   | ((128u >> 4) << 24);         // M = 128
-            const uint32_t ring_n = p.ring, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nsub = p.nsub;
-            const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4;
-            const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
-            const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
-            const uint32_t a_step = p.np == 16 ? 2u : 1u;          // ring slots consumed per K step
-            const uint32_t desc_hi = (128u >> 4) | (1u << 14);     // SBO = 128 B, version = 1
-            const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
-            const uint32_t b_lo0 = ((smem_u32(btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
-            const uint32_t bars_a_full = smem_u32(a_full), bars_a_empty = smem_u32(a_empty);
-            mbar_wait(bar_btile, 0);
-            uint32_t s_first = 0;                 // ring slot of the output row's first page row
-            uint32_t s_new = n_hp - 1, par_new = 0;  // slot/parity of the newest page row the output needs
-            while (s_new >= ring_n) s_new -= ring_n, par_new ^= 1;
-            uint32_t buf = 0, bpar = 0;
-            bool first_round = true;
-            Item it;
-            for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
-                const int n_out_rows = it.ys1 - it.ys0;
-                for (int j = 0; j < n_out_rows; j++) {
-                    mbar_wait_addr<20>(bars_a_full + s_new * 8, par_new);
-                    for (uint32_t sub = 0; sub < nsub; sub++) {
-                        if (!first_round) mbar_wait<20>(t_empty + buf, bpar ^ 1);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + buf * p.nbs;
-                        uint32_t s = s_first, b_lo = b_lo0 + sub * (uint32_t)p.n_mma;  // template n sits n*16 B into a K chunk
-                        for (uint32_t k = 0; k < ksteps; k++) {
-                            const uint64_t adesc = ((uint64_t)desc_hi << 32) | (a_lo0 + s * pitch16);
-                            const uint64_t bdesc = ((uint64_t)desc_hi << 32) | b_lo;
-                            tc_mma_i8(d_tmem, adesc, bdesc, idesc, k);
-                            s += a_step;
-                            if (s >= ring_n) s -= ring_n;
-                            b_lo += 2 * b_lbo16;
-                        }
-                        tc_commit(t_full + buf);                     // accumulator ready for the epilogue
-                        if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
-                    }
-                    tc_commit_addr(bars_a_empty + s_first * 8);      // row s_first is not needed by later outputs
-                    if (++s_first == ring_n) s_first = 0;
-                    if (++s_new == ring_n) s_new = 0, par_new ^= 1;
-                }
-                // the last n_hp-1 rows of the item are never the first row of an output: release them too
-                for (uint32_t r = 0; r + 1 < n_hp; r++) {
-                    tc_commit_addr(bars_a_empty + s_first * 8);
-                    if (++s_first == ring_n) s_first = 0;
-                    if (++s_new == ring_n) s_new = 0, par_new ^= 1;
-                }
-            }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ================================================================== Toeplitz expansion
-        const int e = threadIdx.x - 128;  // window index 0..127
-        const bool mirror = p.np == 16;
-        const uint32_t ring_n = p.ring;
-        uint32_t rs = 0, rpar = 0, s = 0, spar = 1;
+        const uint32_t row_bytes = 128 + p.np;
+        uint32_t rg = 0, rgpar = 1;  // raw group and the parity of its PREVIOUS use
+        uint32_t in_group = 0, slot = 0;
         bool first_round = true;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+            const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0 + (size_t)it.ys0 * p.pitch;
             const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
-            for (int r = 0; r < n_rows; r++) {
-                mbar_wait<100>(raw_full + rs, rpar);
-                if (!first_round) mbar_wait<100>(a_empty + s, spar);
-                const uint32_t *rw = (const uint32_t *)(raw + rs * TC_RAW_BYTES);
+            for (int r = 0; r < n_rows; r++, src += p.pitch) {
+                if (in_group == 0 && !first_round) mbar_wait<200>(raw_empty + rg, rgpar);
+                if (elect_one()) {
+                    mbar_expect_tx(raw_full + rg, row_bytes);
+                    tma_bulk_g2s(raw + slot * TC_RAW_BYTES, src, row_bytes, raw_full + rg);
+                    if (in_group == TC_G - 1) mbar_arrive(raw_full + rg);
+                }
+                __syncwarp();
+                slot++;
+                if (++in_group == TC_G) {
+                    in_group = 0;
+                    if (++rg == TC_RAW_GROUPS) rg = 0, slot = 0, rgpar ^= 1, first_round = false;
+                }
+            }
+        }
+        if (in_group != 0 && elect_one()) mbar_arrive(raw_full + rg);  // the last, partial group
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        // Warp-uniform control flow (the loop state stays in uniform registers, no R2UR / ELECT loops
+        // around every UTCIMMA) and no divisions: a single warp issues all tensor work of the SM, so
+        // its instruction count per tcgen05.mma bounds the kernel once the other roles keep up.
+        const uint32_t idesc = (2u << 4)                         // D format: S32
+                               | (0u << 7) | (0u << 10)          // A, B: unsigned 8-bit
+                               | (0u << 15) | (0u << 16)         // A, B: K-major
+                               | ((uint32_t)(p.n_mma >> 3) << 17)  // N
+                               | ((128u >> 4) << 24);            // M = 128
+        const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp,
+                       nsub = p.nsub;
+        const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4;
+        const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
+        const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
+        const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // SBO = 128 B, version = 1
+        const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
+        const uint32_t b_lo0 = ((smem_u32(btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+        mbar_wait(bar_btile, 0);
+        uint32_t s_first = 0;                    // ring slot of the output row's first page row
+        uint32_t rel_in_group = 0, rel_g = 0;    // release bookkeeping: position of s_first inside its group
+        uint32_t new_in_group = 0, new_g = 0, new_par = 0;  // group of the NEXT not-yet-awaited page row
+        uint32_t rows_ready = 0, rows_needed = n_hp;         // page rows known to be expanded / needed by this output
+        uint32_t buf = 0, bpar = 0;
+        bool first_round = true;
+        Item it;
+        for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+            const int n_out_rows = it.ys1 - it.ys0;
+            // Two accumulators are always in flight: consecutive tcgen05.mma into the SAME accumulator
+            // serialise on the accumulate dependency (~100 cycles each, measured), so the K steps of two
+            // independent jobs are interleaved -- the two column halves of one output row when nsub == 2,
+            // else two consecutive output rows.
+            for (int j = 0; j < n_out_rows;) {
+                const bool two_rows = nsub == 1 && j + 1 < n_out_rows;
+                const uint32_t njobs = nsub == 2 ? 2u : (two_rows ? 2u : 1u);
+                const uint32_t need = rows_needed + (two_rows ? 1u : 0u);
+                while (rows_ready < need) {   // at most once per 4 output rows in steady state
+                    mbar_wait<20>(a_full + new_g, new_par);
+                    rows_ready += TC_G;
+                    if (++new_g == ring_g) new_g = 0, new_par ^= 1;
+                }
+                uint32_t buf1 = buf + 1, bpar1 = bpar;
+                bool first1 = first_round;
+                if (buf1 == nbuf) buf1 = 0, bpar1 ^= 1, first1 = false;
+                if (!first_round) mbar_wait<20>(t_empty + buf, bpar ^ 1);
+                if (njobs == 2 && !first1) mbar_wait<20>(t_empty + buf1, bpar1 ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d0 = tmem_base + buf * p.nbs, d1 = tmem_base + buf1 * p.nbs;
+                    uint32_t s0 = s_first, s1 = s_first + (two_rows ? 1u : 0u);
+                    if (s1 >= ring_n) s1 -= ring_n;
+                    uint32_t bl0 = b_lo0, bl1 = b_lo0 + (nsub == 2 ? (uint32_t)p.n_mma : 0u);  // template n sits n*16 B into a K chunk
+                    for (uint32_t k = 0; k < ksteps; k++) {
+                        tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | (a_lo0 + s0 * pitch16), ((uint64_t)desc_hi << 32) | bl0, idesc, k);
+                        if (k + 1 == ksteps) tc_commit(t_full + buf);       // accumulator ready for the epilogue
+                        if (njobs == 2) {
+                            tc_mma_i8(d1, ((uint64_t)desc_hi << 32) | (a_lo0 + s1 * pitch16), ((uint64_t)desc_hi << 32) | bl1, idesc, k);
+                            if (k + 1 == ksteps) tc_commit(t_full + buf1);
+                        }
+                        s0 += a_step;
+                        if (s0 >= ring_n) s0 -= ring_n;
+                        s1 += a_step;
+                        if (s1 >= ring_n) s1 -= ring_n;
+                        bl0 += 2 * b_lbo16;
+                        bl1 += 2 * b_lbo16;
+                    }
+                }
+                __syncwarp();
+                for (uint32_t q2 = 0; q2 < njobs; q2++)
+                    if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
+                // released page rows: a whole group is handed back to the expansion warps at once
+                const int rows_done = two_rows ? 2 : 1;
+                for (int q2 = 0; q2 < rows_done; q2++) {
+                    if (++rel_in_group == TC_G) {
+                        if (elect_one()) tc_commit(a_empty + rel_g);
+                        __syncwarp();
+                        rel_in_group = 0;
+                        if (++rel_g == ring_g) rel_g = 0;
+                    }
+                    if (++s_first == ring_n) s_first = 0;
+                    rows_needed++;
+                }
+                j += rows_done;
+            }
+            // the last n_hp-1 rows of the item are never the first row of an output: release them too
+            for (uint32_t r = 0; r + 1 < n_hp; r++) {
+                if (++rel_in_group == TC_G) {
+                    if (elect_one()) tc_commit(a_empty + rel_g);
+                    __syncwarp();
+                    rel_in_group = 0;
+                    if (++rel_g == ring_g) rel_g = 0;
+                }
+                if (++s_first == ring_n) s_first = 0;
+                rows_needed++;
+            }
+        }
+        (void)new_in_group;
+    } else if (warp >= 4 && warp < 8) {
+        // ================================================================== Toeplitz expansion
+        // one warp per page row, four rows (one group) in flight per handshake
+        const int w = warp - 4;
+        const bool mirror = p.np == 16;
+        const uint32_t ring_g = p.ring_groups;
+        uint32_t rg = 0, rgpar = 0, ag = 0, agpar = 1;
+        bool first_round = true;
+        for (uint32_t g0 = 0; g0 < total_rows; g0 += TC_G) {
+            mbar_wait<100>(raw_full + rg, rgpar);
+            if (!first_round) mbar_wait<100>(a_empty + ag, agpar);
+            if (g0 + w < total_rows) {
+                const uint32_t *rw = (const uint32_t *)(raw + (rg * TC_G + w) * TC_RAW_BYTES);
+                const uint32_t s = ag * TC_G + w;
                 uint8_t *dst = ring + (size_t)s * p.row_pitch;
-                for (int ee = e; ee < p.n_entries; ee += 128) {
-                    const uint32_t *w = rw + (ee >> 2);
+                for (int ee = lane; ee < p.n_entries; ee += 32) {
+                    const uint32_t *wp = rw + (ee >> 2);
                     const int sh = (ee & 3) * 8;
-                    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
                     uint4 o;
                     o.x = __funnelshift_r(w0, w1, sh);
                     o.y = __funnelshift_r(w1, w2, sh);
                     o.z = __funnelshift_r(w2, w3, sh);
                     o.w = __funnelshift_r(w3, w4, sh);
                     *(uint4 *)(dst + ee * 16) = o;
-                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)ring_n * p.row_pitch + ee * 16) = o;
+                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)p.ring * p.row_pitch + ee * 16) = o;
                 }
-                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
-                mbar_arrive(a_full + s);
-                mbar_arrive(raw_empty + rs);
-                if (++rs == TC_RAW_SLOTS) rs = 0, rpar ^= 1;
-                if (++s == ring_n) s = 0, spar ^= 1, first_round = false;
             }
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(a_full + ag);
+                mbar_arrive(raw_empty + rg);
+            }
+            if (++rg == TC_RAW_GROUPS) rg = 0, rgpar ^= 1;
+            if (++ag == ring_g) ag = 0, agpar ^= 1, first_round = false;
         }
     } else if (warp >= 8) {
-        // ================================================================== epilogue
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int grp = (warp - 8) >> 2;          // chunk ch belongs to group ch % TC_EPI_GROUPS
+        // ================================================================== epilogue (16 warps)
+        // 4 warps per TMEM lane quarter (= per SM sub-partition); the 32-column units of the accumulator
+        // buffers are dealt round-robin to the 4 warps ACROSS buffers so they stay balanced.
+        const int e = warp - 8;
+        const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
+        const int grp = e >> 2;
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t nbuf = p.nbuf;
-        const int nunits = p.nunits, urot = p.nunits % TC_EPI_GROUPS;
-        int ufirst = grp;  // first unit of the current buffer that belongs to this group
+        const int nunits = p.nunits, nsub = p.nsub, urot = p.nunits % TC_EPI_GROUPS;
+        int ufirst = grp;  // first unit of the current buffer that belongs to this warp
         uint32_t buf = 0, bpar = 0;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
@@ -463,39 +569,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 P = __ldg(p.pf + plane + (size_t)it.ys0 * p.spitch);
             }
             for (int y = it.ys0; y < it.ys1; y++) {
-                uint32_t s_next = 0;  // prefetch the next row's window statistics
+                uint32_t s_next = 0;  // prefetch the next row's window statistics (issued now, used next row)
                 float P_next = 0.f;
                 if (x_ok && y + 1 < it.ys1) {
-                    s_next = __ldg(p.sp + plane + (size_t)(y + 1) * p.spitch);
-                    P_next = __ldg(p.pf + plane + (size_t)(y + 1) * p.spitch);
+                    s_next = ldg_now_u32(p.sp + plane + (size_t)(y + 1) * p.spitch);
+                    P_next = ldg_now_f32(p.pf + plane + (size_t)(y + 1) * p.spitch);
                 }
                 const bool valid = x_ok && P < __int_as_float(0x7f800000);  // +inf marks a constant window
                 const float S = (float)s_p;
                 const float Pv = valid ? P : 0.f;
                 const unsigned long long SS = pack2(S, S), PP = pack2(Pv, Pv);
-                for (int sub = 0; sub < p.nsub; sub++) {
+                for (int sub = 0; sub < nsub; sub++) {
                     mbar_wait(t_full + buf, bpar);
                     tc_fence_after();
                     const uint32_t tb = tlane + buf * p.nbs;
                     const int cbase = sub * p.n_mma;
-                    // this group's 16-column units of the buffer, software pipelined: the TMEM load of
-                    // the next unit is in flight while the current one is filtered
-                    int u = ufirst;
-                    if (u < nunits) {
-                        uint32_t va[16], vb[16];
-                        tc_ld16(tb + u * 16, va);
-                        while (true) {
-                            tc_wait_ld();
-                            const int u1 = u + TC_EPI_GROUPS;
-                            if (u1 < nunits) tc_ld16(tb + u1 * 16, vb);
-                            handle_unit(p, cst_s, tb + u * 16, cbase + u * 16, va, SS, PP, valid, it.page, gx, y);
-                            if (u1 >= nunits) break;
-                            tc_wait_ld();
-                            const int u2 = u1 + TC_EPI_GROUPS;
-                            if (u2 < nunits) tc_ld16(tb + u2 * 16, va);
-                            handle_unit(p, cst_s, tb + u1 * 16, cbase + u1 * 16, vb, SS, PP, valid, it.page, gx, y);
-                            if (u2 >= nunits) break;
-                            u = u2;
+                    if (p.dbg_mode != 1) {
+                        for (int u = ufirst; u < nunits; u += TC_EPI_GROUPS) {
+                            uint32_t v[32];
+                            tc_ld32(tb + u * 32, v);
+                            tc_wait_ld32(v);
+                            handle_unit(p, cst_s, tb + u * 32, cbase + u * 32, v, SS, PP, valid, it.page, gx, y);
                         }
                     }
                     if (p.dbg_acc && p.dbg_col >= cbase && p.dbg_col < cbase + p.n_mma && grp == 0) {
@@ -507,7 +601,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + buf);
                     if (++buf == nbuf) buf = 0, bpar ^= 1;
-                    // round-robin the units over the groups ACROSS buffers so the groups stay balanced
                     ufirst -= urot;
                     if (ufirst < 0) ufirst += TC_EPI_GROUPS;
                 }
@@ -582,7 +675,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int row_pitch)
 {
     return ((btile_bytes + 127) & ~127u) + (size_t)(ring + 1) * row_pitch + TC_RAW_SLOTS * TC_RAW_BYTES +
-           (1 + 2 * TC_RAW_SLOTS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 64 + 128 * 16;
+           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 64 + 128 * 16;
 }
 
 int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
@@ -596,9 +689,10 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     const uint32_t n_hp = np == 16 ? (n_h + 1) & ~1u : n_h;
     tc.kchunks = n_h * (np / 16);
     tc.ksteps = (tc.kchunks + 1) / 2;
-    const int ring = (int)n_hp + TC_LOOK;
+    const int ring_groups = ((int)n_hp + 1 + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;
+    const int ring = ring_groups * TC_G;
     const int row_pitch = np == 16 ? 2048 : 2304;
-    if (ring > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
+    if (ring_groups > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
     // largest NB (multiple of 16, <= 256) whose B tile fits next to the ring
     int nb_max = 256;
     while (nb_max >= 16 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, row_pitch) > TC_SMEM_BUDGET) nb_max -= 16;
@@ -666,12 +760,15 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
     p.ksteps = tc.ksteps;
     p.nb = tc.nb;
-    p.nsub = tc.nb > 128 ? 2 : 1;           // tc_class_build makes nb a multiple of 32 when it exceeds 128
+    // one MMA covers all nb columns: a tcgen05.mma carries ~100 cycles of fixed cost (measured), so fewer,
+    // wider instructions win over finer TMEM buffering; FOCR_TC_NSUB2 re-enables the split for experiments
+    p.nsub = (tc.nb > 128 && getenv("FOCR_TC_NSUB2")) ? 2 : 1;
     p.n_mma = tc.nb / p.nsub;
-    p.nunits = p.n_mma / 16;
+    p.nunits = (p.n_mma + 31) / 32;
     p.nbs = (p.n_mma + 31) & ~31;
     p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
-    p.ring = p.n_hp + TC_LOOK;
+    p.ring_groups = (p.n_hp + 1 + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;  // rows y..y+n_hp (two output rows in flight) may straddle one more group
+    p.ring = p.ring_groups * TC_G;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
     p.n_entries = tc.np == 16 ? 128 : 144;
     p.btile_bytes = 2 * tc.ksteps * tc.nb * 16;
@@ -697,6 +794,10 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     const float up = 1.0f + 1.0f / 4096.0f, dn = 1.0f - 1.0f / 4096.0f;
     const std::vector<float2> &cst = *(const std::vector<float2> *)tc.consts_host;
     p.dbg_acc = dbg_acc;
+    {
+        const char *dm = getenv("FOCR_TC_DBG");
+        p.dbg_mode = dm ? atoi(dm) : 0;
+    }
     p.dbg_col = dbg_acc ? dbg_pos % (int)tc.nb : -1;
     for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
