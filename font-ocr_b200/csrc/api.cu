@@ -25,6 +25,8 @@ static int fail(int code, const std::string &msg)
     g_err = msg;
     return code;
 }
+// shared with focr_decode.cu
+int focr_internal_fail(int code, const std::string &msg) { return fail(code, msg); }
 #define CU(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e_ = (call);                                                                     \
@@ -205,6 +207,8 @@ extern "C" int focr_ctx_sync(focr_ctx *c)
     return FOCR_OK;
 }
 extern "C" uint64_t focr_ctx_launch_count(const focr_ctx *c) { return c ? c->launches : 0; }
+int focr_internal_device(const focr_ctx *c) { return c->device; }
+void focr_internal_count_launch(focr_ctx *c, int n) { c->launches += n; }
 extern "C" int focr_ctx_profile(focr_ctx *c, int enable)
 {
     if (!c) return fail(FOCR_ERR_ARG, "focr_ctx_profile: NULL");

@@ -72,7 +72,7 @@ def lib():
     l.focr_ncc_scan_device.argtypes = [vp, vp, vp, sz, sz, u32, u32, u32, C.c_float, u32, vp, vp]
     l.focr_window_stats.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp]
     l.focr_ncc_numerators.argtypes = [vp, vp, u32, vp, u32, u32, vp]
-    l.focr_glyph_bank_create.argtypes = [vp, vp, sz, vp, vp, u32, C.POINTER(vp)]
+    l.focr_glyph_bank_create.argtypes = [vp, vp, sz, vp, vp, u32, C.c_int32, C.POINTER(vp)]
     l.focr_glyph_bank_destroy.argtypes = [vp]
     l.focr_glyph_bank_destroy.restype = None
     l.focr_decode_pages.argtypes = [vp, vp, vp, sz] + [u32] * 10 + [vp, vp, vp, vp]

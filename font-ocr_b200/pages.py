@@ -81,23 +81,39 @@ def focr_render_line(font: Font, text: str, size: float, kern_x: float = 1.0):
 def make_focr_page(font: Font, size: float, width: int, height: int, seed: int = 0, x_start: int = 45,
                    y_start: int = 39, line_width: int = 608, line_height: int = 12, line_advance: int = 15,
                    fill: float = 1.0, alphabet: str | None = None):
-    """A page of base64 lines placed where focr's rectangles look (main.rs:199-203): line i is
-    rendered with the reference's own layout and pasted so that its canvas top-left lands on
-    (x_start, y_start + i*line_advance).  Returns (gray u8, lines)."""
+    """A page of base64 lines placed where focr's rectangles look (main.rs:199-203).  Line i is laid
+    out with the reference's own pen arithmetic (main.rs:46-54: f32 advances) and rasterised with the
+    origin decode_line uses (main.rs:133-147: minus the alphabet's raster-bounds origin), clipped to
+    the (line_width x line_height) rectangle at (x_start, y_start + i*line_advance).
+    Returns (gray u8, lines)."""
+    from .raster import FOCR_DEFAULT_ALPHABET
+
+    alphabet = alphabet or FOCR_DEFAULT_ALPHABET
     ink = np.zeros((height, width), np.uint8)
     n_lines = max(int(((height - y_start - line_height) // line_advance) * fill), 0)
-    # characters per line: keep the rendered line inside line_width
-    avg = float(np.mean([font.advance(font.glyph_for_char(c))[0] for c in "ABCDEFGHIJabcdefghij0123456789+/"]))
-    per_line = max(int(line_width / (avg / font.units_per_em * size)) - 4, 1)
-    text = base64_text(seed, per_line * max(n_lines, 1))
+    gids = {c: font.glyph_for_char(c) for c in alphabet}
+    x0 = y0 = 0
+    for gid in gids.values():
+        a, b, _, _ = font.raster_bounds(gid, size, 0.0, 0.0)
+        x0, y0 = min(x0, a), min(y0, b)
+    ox, oy = f32(-x0), f32(-y0)
+    upem = f32(font.units_per_em)
+    body = [c for c in alphabet if c in "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/"]
+    avg = float(np.mean([font.advance(gids[c])[0] for c in body])) / font.units_per_em * size
+    per_line = max(int((line_width - 8) / avg) - 4, 1)
+    rng = np.random.default_rng(seed)
     lines = []
     for li in range(n_lines):
-        line = "> " + text[li * per_line:(li + 1) * per_line]
-        canvas, _ = focr_render_line(font, line, size)
-        canvas = canvas[:line_height, :line_width]
+        line = "> " + "".join(body[i] for i in rng.integers(0, len(body), per_line))
+        canvas = np.zeros((line_height, line_width), np.uint8)
+        pos = f32(0.0)
+        for ch in line:
+            g = np.zeros_like(canvas)
+            font.rasterize_glyph(g, gids[ch], size, f32(ox + pos), oy)
+            np.maximum(canvas, g, out=canvas)
+            pos = f32(pos + f32(f32(font.advance(gids[ch])[0] / upem) * f32(size)))
         y = y_start + li * line_advance
-        h, w = canvas.shape
-        h, w = min(h, height - y), min(w, width - x_start)
+        h, w = min(line_height, height - y), min(line_width, width - x_start)
         if h <= 0 or w <= 0:
             break
         np.maximum(ink[y:y + h, x_start:x_start + w], canvas[:h, :w], out=ink[y:y + h, x_start:x_start + w])

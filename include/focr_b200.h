@@ -146,16 +146,20 @@ int focr_ncc_numerators(focr_ctx *ctx, const focr_bank *bank, uint32_t t, const 
 /* ------------------------------------------------------------------------------------------
  * Section 3 -- focr least-squared-distance line decode (main.rs:87-181 on the device).
  *
- * The glyph bank is the (glyph, subpixel shift) raster cache README.md:44 asks for: for each glyph
- * g < n_glyphs (alphabet order, main.rs:125-128) and each of the 64 horizontal 26.6 sub-pixel
- * phases s, the FreeType bitmap of g at pen fraction s/64 with its placement relative to the
- * integer pen position on the line canvas (left = bitmap_left, top = -bitmap_top + origin.y, both
- * already including `origin` of main.rs:147).  advance_px[g] is
- * `advance(g).x / units_per_em * size * kern_x` evaluated in f32 in that order (main.rs:176-178).
+ * The glyph bank is the (glyph, subpixel shift) raster cache README.md:44 asks for.  font-kit hands
+ * FreeType the translation `origin + pos` (main.rs:102) as a 26.6 delta `d = (int)(tx * 64.0f)`
+ * (f32 arithmetic, truncation); the bitmap only depends on the phase d & 63 and moves by whole pixels
+ * with d >> 6.  So for each glyph g < n_glyphs (alphabet order, main.rs:125-128) and each phase
+ * s in 0..63 the bank holds the FreeType bitmap rendered with delta (s, -origin.y*64) and its
+ * placement on the line canvas for d >> 6 == 0: left = bitmap_left, top = -bitmap_top.
+ * origin_x is main.rs:147's origin.x (an integer: minus the left edge of the alphabet's raster
+ * bounds); the kernel evaluates d from f32(origin_x + pos) exactly like the host would.
+ * advance_px[g] is `advance(g).x / units_per_em * size * kern_x` evaluated in f32 in that order
+ * (main.rs:176-178).
  * ------------------------------------------------------------------------------------------ */
 typedef struct focr_glyph_raster {
     uint64_t offset;    /* into `pixels`: rows tightly packed, w*h bytes */
-    int16_t left, top;  /* top-left of the bitmap on the line canvas for integer pen x == 0 */
+    int16_t left, top;  /* top-left of the bitmap on the line canvas when (d >> 6) == 0 */
     uint16_t w, h;
 } focr_glyph_raster;
 
@@ -163,7 +167,7 @@ typedef struct focr_glyph_bank focr_glyph_bank;
 
 int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size_t n_pixel_bytes,
                            const focr_glyph_raster *rasters /* [n_glyphs][64] */, const float *advance_px,
-                           uint32_t n_glyphs, focr_glyph_bank **out);
+                           uint32_t n_glyphs, int32_t origin_x, focr_glyph_bank **out);
 void focr_glyph_bank_destroy(focr_glyph_bank *bank);
 
 /* Decode rectangles (x_start, y_start + i*line_advance, width, line_height), i = 0.. of each page
