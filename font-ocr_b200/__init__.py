@@ -5,6 +5,7 @@ Layout (DESIGN.md has the full map):
   host/      C++ mirror of the reference's host-side operators (Searcher, process_hits, decode_line)
   ncc.py     ctypes binding + Python mirror of the reference interface for the NCC path
   focr.py    same for the focr path
+  shard.py   page sharding across GPUs + host-side gather (no data-path collective)
   raster.py  FreeType template/glyph-bank producer (the (glyph, subpixel shift) raster cache)
   pages.py   synthetic page generator for the BASELINE configs
 
@@ -13,11 +14,11 @@ library is missing.  The CPU restatement lives in oracle/ and is test infrastruc
 """
 from . import raster, pages  # noqa: F401  (pure host-side; importable without the CUDA library)
 
-__all__ = ["raster", "pages", "ncc", "focr", "native"]
+__all__ = ["raster", "pages", "shard", "ncc", "focr", "native"]
 
 
 def __getattr__(name):
-    if name in ("ncc", "focr", "native"):
+    if name in ("ncc", "focr", "native", "shard"):
         import importlib
 
         return importlib.import_module(f"{__name__}.{name}")

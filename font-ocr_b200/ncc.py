@@ -213,3 +213,38 @@ def process_hits(all_hits, anchor_threshold: float = 0.95, overlap: int = 5):
 
 def lines_to_text(lines):
     return ["".join(h[0] for h in line) for line in lines]
+
+
+def host_process_hits(all_hits, anchor_threshold: float = 0.95, overlap: int = 5):
+    """process_hits through the C++ host mirror (host/focr_host.cpp); same input/output as process_hits.
+    Raises IndexError where the reference panics (no anchor line, ncc.rs:1040)."""
+    n = len(all_hits)
+    xs = np.array([h[1] for h in all_hits], np.int32)
+    ys = np.array([h[2] for h in all_hits], np.int32)
+    sims = np.array([h[3] for h in all_hits], np.float32)
+    letters = np.array([ord(h[0]) for h in all_hits], np.uint32)
+    out_index = np.zeros(max(n, 1), np.uint32)
+    line_offsets = np.zeros(n + 2, np.uint32)
+    n_lines = np.zeros(1, np.uint32)
+    rc = lib().focr_host_process_hits(ptr(xs), ptr(ys), ptr(sims), ptr(letters), n, C.c_float(anchor_threshold),
+                                      overlap, ptr(out_index), ptr(line_offsets), ptr(n_lines))
+    if rc != native.FOCR_OK:
+        msg = lib().focr_last_error().decode()
+        if msg.startswith("panic:"):
+            raise IndexError(msg)
+        raise native.FocrError(rc, msg)
+    return [[all_hits[i] for i in out_index[line_offsets[l]:line_offsets[l + 1]]] for l in range(int(n_lines[0]))]
+
+
+def host_search_c_u8(gray: np.ndarray, needle: np.ndarray, threshold: float):
+    """Searcher::new + search_c_u8 through the C++ host mirror."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    needle = np.ascontiguousarray(needle, np.uint8)
+    out = np.zeros(MAX_MATCHES, MATCH_DTYPE)
+    n = np.zeros(1, np.uint32)
+    rc = lib().focr_host_search_c_u8(ptr(gray), gray.shape[1], gray.shape[0], ptr(needle), needle.shape[1],
+                                     needle.shape[0], C.c_float(threshold), ptr(out), ptr(n))
+    if rc == native.FOCR_ERR_UNSUPPORTED:
+        raise NotImplementedError(lib().focr_last_error().decode())
+    check(rc)
+    return out[:n[0]].copy()

@@ -188,6 +188,25 @@ int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t 
 int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys_host, size_t len,
                         uint32_t n_pairs, int64_t *out_host);
 
+/* ------------------------------------------------------------------------------------------
+ * Section 4 -- C hooks into the C++ host mirror (font-ocr_b200/host/focr_host.hpp), used by tests.
+ * The mirror itself (Searcher, get_hits, process_hits, partition_by, decode_image_vec) is a C++
+ * API with the reference's names; these two entries expose it to ctypes.
+ * ------------------------------------------------------------------------------------------ */
+/* process_hits (ncc.rs:723-786) on n hits given in get_hits order.  out_index receives, line after
+ * line, the indices (into the input arrays) of the hits that survive; line l is
+ * out_index[line_offsets[l] .. line_offsets[l+1]).  out_index and line_offsets need n and n+1
+ * entries.  Where the reference panics (no anchor line at all -> partition_by on an empty slice,
+ * ncc.rs:1040) the call returns FOCR_ERR_ARG with "panic: ..." in focr_last_error(). */
+int focr_host_process_hits(const int32_t *xs, const int32_t *ys, const float *sims, const uint32_t *letters,
+                           uint32_t n, float anchor_threshold, int32_t overlap, uint32_t *out_index,
+                           uint32_t *line_offsets, uint32_t *n_lines);
+/* Searcher::new + Searcher::search_c_u8 (ncc.rs:231-261, 332-404) for one gray page and one tight
+ * n_w x n_h needle; out needs 1024 entries.  Widths above 16 return FOCR_ERR_UNSUPPORTED
+ * ("panic: not handled", ncc.rs:392). */
+int focr_host_search_c_u8(const uint8_t *gray, uint32_t r_w, uint32_t r_h, const uint8_t *needle, uint32_t n_w,
+                          uint32_t n_h, float threshold, focr_match *out, uint32_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -191,3 +191,17 @@ def test_full_size_page_properties_and_sample(kctx, oracle, font, pkg):
     for t in sample:
         exp = s.search_c_u8(tpls[t], 0.8)
         _assert_same(m[0, t:t + 1], c[0, t:t + 1], [exp], f"template {t}")
+
+
+def test_cpp_host_searcher_matches_golden(ctx, golden):
+    """The C++ Searcher mirror (host/focr_host.cpp) marshals like ncc.rs:332-404 and reproduces the
+    reference's match lists; widths above 16 'panic' like ncc.rs:392."""
+    from font_ocr_b200 import ncc
+
+    for t in (0, 33, 70):
+        n = int(golden["text16_counts"][t])
+        off = int(golden["text16_counts"][:t].sum())
+        got = ncc.host_search_c_u8(golden["text16_page"], golden["text16_tpl"][t], 0.8)
+        assert got.tobytes() == golden["text16_hits"][off:off + n].tobytes(), t
+    with pytest.raises(NotImplementedError):
+        ncc.host_search_c_u8(golden["text16_page"], np.zeros((5, 17), np.uint8), 0.8)
