@@ -46,6 +46,7 @@ constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side m
 constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
 constexpr int TC_YSEG = 128;          // output rows per work item
+constexpr int TC_ST_DEPTH = 8;        // rows of window statistics each epilogue warp streams ahead (cp.async ring)
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
@@ -209,6 +210,16 @@ __device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
                    "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ uint32_t ldg_now_u32(const uint32_t *p)
 {
     uint32_t v;  // volatile: issue the load HERE (the compiler would otherwise sink a prefetch to its use)
@@ -338,6 +349,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
     // 128 x {-b'_2i, -b'_2i+1, -a'_2i, -a'_2i+1}; offset arithmetic on `smem` keeps it a shared-space pointer (LDS.128)
     float4 *cst_s = (float4 *)(smem + (((size_t)((uint8_t *)(tmem_ptr + 4) - smem) + 15) & ~(size_t)15));
+    uint32_t *st_ring = (uint32_t *)(cst_s + 128);  // [16 epilogue warps][TC_ST_DEPTH][2][32]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -457,22 +469,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 if (!first_round) mbar_wait<20>(t_empty + buf, bpar ^ 1);
                 if (njobs == 2 && !first1) mbar_wait<20>(t_empty + buf1, bpar1 ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
+                {
+                    // All lanes run the (warp-uniform) descriptor arithmetic so that it stays on the uniform
+                    // datapath; only the tcgen05 instructions themselves are predicated on the elected lane.
+                    const bool leader = elect_one();
                     const uint32_t d0 = tmem_base + buf * p.nbs, d1 = tmem_base + buf1 * p.nbs;
                     uint32_t s0 = s_first, s1 = s_first + (two_rows ? 1u : 0u);
                     if (s1 >= ring_n) s1 -= ring_n;
+                    uint32_t al0 = a_lo0 + s0 * pitch16, al1 = a_lo0 + s1 * pitch16;
+                    const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
                     uint32_t bl0 = b_lo0, bl1 = b_lo0 + (nsub == 2 ? (uint32_t)p.n_mma : 0u);  // template n sits n*16 B into a K chunk
                     for (uint32_t k = 0; k < ksteps; k++) {
-                        tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | (a_lo0 + s0 * pitch16), ((uint64_t)desc_hi << 32) | bl0, idesc, k);
-                        if (k + 1 == ksteps) tc_commit(t_full + buf);       // accumulator ready for the epilogue
-                        if (njobs == 2) {
-                            tc_mma_i8(d1, ((uint64_t)desc_hi << 32) | (a_lo0 + s1 * pitch16), ((uint64_t)desc_hi << 32) | bl1, idesc, k);
-                            if (k + 1 == ksteps) tc_commit(t_full + buf1);
+                        if (leader) {
+                            tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | al0, ((uint64_t)desc_hi << 32) | bl0, idesc, k);
+                            if (k + 1 == ksteps) tc_commit(t_full + buf);       // accumulator ready for the epilogue
+                            if (njobs == 2) {
+                                tc_mma_i8(d1, ((uint64_t)desc_hi << 32) | al1, ((uint64_t)desc_hi << 32) | bl1, idesc, k);
+                                if (k + 1 == ksteps) tc_commit(t_full + buf1);
+                            }
                         }
-                        s0 += a_step;
-                        if (s0 >= ring_n) s0 -= ring_n;
-                        s1 += a_step;
-                        if (s1 >= ring_n) s1 -= ring_n;
+                        al0 += a_inc;
+                        if (al0 >= a_end) al0 -= a_wrap;
+                        al1 += a_inc;
+                        if (al1 >= a_end) al1 -= a_wrap;
                         bl0 += 2 * b_lbo16;
                         bl1 += 2 * b_lbo16;
                     }
@@ -562,18 +581,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             const int gx = it.x0 + m;
             const bool x_ok = gx >= 1 && gx <= p.r_w - p.n_w;  // ncc.rs:281: x starts at 1
             const size_t plane = (size_t)it.page * p.plane_page_stride + gx;
-            uint32_t s_p = 0;
-            float P = 0.f;
-            if (x_ok) {
-                s_p = __ldg(p.sp + plane + (size_t)it.ys0 * p.spitch);
-                P = __ldg(p.pf + plane + (size_t)it.ys0 * p.spitch);
+            // Window statistics (s_p, norm_p) of this lane's window: streamed TC_ST_DEPTH rows ahead through a
+            // private shared-memory ring with cp.async.  (Register prefetching does not work here: rotating
+            // the registers makes the compiler wait for the in-flight load one row after it was issued,
+            // and a row can take less than an L2 round trip.)  Every lane reads back only what it copied
+            // itself, so cp.async.wait_group is all the synchronisation needed.
+            const uint32_t *sp_col = p.sp + plane;
+            const float *pf_col = p.pf + plane;
+            uint32_t *st_mine = st_ring + (size_t)e * TC_ST_DEPTH * 64 + lane;
+            int st_slot = 0;
+#pragma unroll 1
+            for (int d = 0; d < TC_ST_DEPTH; d++) {
+                const int yy = it.ys0 + d;
+                if (x_ok && yy < it.ys1) {
+                    cp_async4(st_mine + d * 64, sp_col + (size_t)yy * p.spitch);
+                    cp_async4(st_mine + d * 64 + 32, pf_col + (size_t)yy * p.spitch);
+                }
+                cp_async_commit();
             }
             for (int y = it.ys0; y < it.ys1; y++) {
-                uint32_t s_next = 0;  // prefetch the next row's window statistics (issued now, used next row)
-                float P_next = 0.f;
-                if (x_ok && y + 1 < it.ys1) {
-                    s_next = ldg_now_u32(p.sp + plane + (size_t)(y + 1) * p.spitch);
-                    P_next = ldg_now_f32(p.pf + plane + (size_t)(y + 1) * p.spitch);
+                cp_async_wait<TC_ST_DEPTH - 1>();
+                const uint32_t s_p = st_mine[st_slot * 64];
+                const float P = __uint_as_float(st_mine[st_slot * 64 + 32]);
+                {
+                    const int yy = y + TC_ST_DEPTH;
+                    if (x_ok && yy < it.ys1) {
+                        cp_async4(st_mine + st_slot * 64, sp_col + (size_t)yy * p.spitch);
+                        cp_async4(st_mine + st_slot * 64 + 32, pf_col + (size_t)yy * p.spitch);
+                    }
+                    cp_async_commit();
+                    if (++st_slot == TC_ST_DEPTH) st_slot = 0;
                 }
                 const bool valid = x_ok && P < __int_as_float(0x7f800000);  // +inf marks a constant window
                 const float S = (float)s_p;
@@ -604,8 +641,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     ufirst -= urot;
                     if (ufirst < 0) ufirst += TC_EPI_GROUPS;
                 }
-                s_p = s_next;
-                P = P_next;
             }
         }
     }
@@ -675,7 +710,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int row_pitch)
 {
     return ((btile_bytes + 127) & ~127u) + (size_t)(ring + 1) * row_pitch + TC_RAW_SLOTS * TC_RAW_BYTES +
-           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 64 + 128 * 16;
+           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_MAX_BUF) * 8 + 64 + 128 * 16 + 16 * TC_ST_DEPTH * 64 * 4;
 }
 
 int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,

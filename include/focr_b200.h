@@ -188,6 +188,13 @@ int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t 
 int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys_host, size_t len,
                         uint32_t n_pairs, int64_t *out_host);
 
+/* Measurement aid: tcgen05.mma kind::i8 micro-benchmark (csrc/umma_bench.cu).  Every SM issues
+ * iters*ksteps MMAs of M=128, N=n, K=32 (u8 x u8 -> s32) into nacc rotating accumulators;
+ * cycles_per_mma is the median over SMs.  bench.py --measure-int8 uses it for the roofline denominator
+ * (MEASURED_PEAKS.json has no integer tensor peak). */
+int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
+                       double *ms_total);
+
 /* ------------------------------------------------------------------------------------------
  * Section 4 -- C hooks into the C++ host mirror (font-ocr_b200/host/focr_host.hpp), used by tests.
  * The mirror itself (Searcher, get_hits, process_hits, partition_by, decode_image_vec) is a C++
