@@ -455,7 +455,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             // independent jobs are interleaved -- the two column halves of one output row when nsub == 2,
             // else two consecutive output rows.
             for (int j = 0; j < n_out_rows;) {
-                const bool two_rows = nsub == 1 && j + 1 < n_out_rows;
+                // pairing two rows needs two free accumulators at once: only worth it when there are >= 4 buffers
+                const bool two_rows = nsub == 1 && nbuf >= 4 && j + 1 < n_out_rows;
                 const uint32_t njobs = nsub == 2 ? 2u : (two_rows ? 2u : 1u);
                 const uint32_t need = rows_needed + (two_rows ? 1u : 0u);
                 while (rows_ready < need) {   // at most once per 4 output rows in steady state
@@ -729,7 +730,7 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     const int row_pitch = np == 16 ? 2048 : 2304;
     if (ring_groups > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
     // largest NB (multiple of 16, <= 256) whose B tile fits next to the ring
-    int nb_max = 256;
+    int nb_max = getenv("FOCR_TC_NBMAX") ? atoi(getenv("FOCR_TC_NBMAX")) : 256;  // experiment knob
     while (nb_max >= 16 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, row_pitch) > TC_SMEM_BUDGET) nb_max -= 16;
     if (nb_max < 16) return 0;
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
