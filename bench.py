@@ -310,8 +310,23 @@ def run_ours(args):
             bf16, peak_src = 1400.0, "2 x fallback sustained bf16 1.4 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
         peak = 2.0 * bf16
         achieved = ops_eff / (scan_ms / 1e3) / 1e12 if scan_ms > 0 else 0.0
+        # our own tcgen05.mma kind::i8 micro-benchmark, run live (M128 N256 K32 back to back on every SM)
+        int8_peak = None
+        try:
+            import ctypes as C
+            cyc, ms_ = np.zeros(1), np.zeros(1)
+            native.check(native.lib().focr_bench_umma_i8(ctx._h, 256, 7, 4000, 1, native.ptr(cyc), native.ptr(ms_)))
+            int8_peak = 2.0 * 128 * 256 * 32 * 7 * 4000 * 148 / (float(ms_[0]) * 1e-3) / 1e12
+        except Exception:
+            pass
+        traffic = None
+        try:  # per-launch DRAM bytes of the correlation kernel from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_tc_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "ncc scan (" + args.kernel + ")", "ops": "u8 x u8 -> s32 multiply-adds x 2, unpadded n_w*n_h, W_eff windows",
+                    "traffic": traffic, "kernel": "ncc scan (" + args.kernel + ")", "peak_int8_measured": int8_peak,
+                    "frac_of_int8_measured": (achieved / int8_peak) if int8_peak else None, "ops": "u8 x u8 -> s32 multiply-adds x 2, unpadded n_w*n_h, W_eff windows",
                     "achieved_dense_windows": ops_dense / (scan_ms / 1e3) / 1e12 if scan_ms > 0 else 0.0,
                     "avg_launch_ms": scan_ms / max(scan_launches, 1), "launches": scan_launches,
                     "w_eff_over_w_dense": float(np.mean(list(frac_eff.values()))), "peak_source": peak_src,
