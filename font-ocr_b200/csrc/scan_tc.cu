@@ -34,6 +34,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef FOCR_SCALAR_FFMA
+#define FOCR_SCALAR_FFMA 1  // 1: four scalar FFMA per column pair; 0: two packed FFMA2 (measured slower: FFMA2 only issues on the fma-heavy pipe)
+#endif
+
 namespace focr {
 
 constexpr int TC_THREADS = 768;      // 4 service + 4 expansion + 16 epilogue warps
@@ -113,28 +117,38 @@ __device__ __forceinline__ bool elect_one()
         : "=r"(pred));
     return pred != 0;
 }
-template <int SLEEP_NS = 0>
+// Wait for a phase of an mbarrier.  SUSPEND_NS > 0 passes a suspend-time hint to try_wait: the hardware
+// parks the thread (no issue slots taken from the epilogue warps) and wakes it AS SOON AS the phase
+// completes.  (__nanosleep back-off was measured to add ~1 us to every handoff: its granularity is far
+// coarser than the requested 20-200 ns.)
+template <int SUSPEND_NS = 0>
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity)
 {
     uint32_t done;
-    bool first = true;
     do {
-        // service warps back off between probes so their spinning does not take issue slots from the epilogue
-        if (SLEEP_NS > 0 && !first) __nanosleep(SLEEP_NS);
-        first = false;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
+        if (SUSPEND_NS > 0) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity), "r"((uint32_t)SUSPEND_NS)
+                : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
+        }
     } while (!done);
 }
-template <int SLEEP_NS = 0>
+template <int SUSPEND_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    mbar_wait_addr<SLEEP_NS>(smem_u32(bar), parity);
+    mbar_wait_addr<SUSPEND_NS>(smem_u32(bar), parity);
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -312,23 +326,65 @@ __device__ __forceinline__ uint32_t prefilter_unit(const float4 *__restrict__ cs
     return __byte_perm(m1, m0, 0x5410);  // (m0 << 16) | (m1 & 0xFFFF) in one PRMT
 }
 
-__device__ __forceinline__ void handle_unit(const TcParams &p, const float4 *cst_s, uint32_t taddr, int col,
+// Fast screen of a 32-column unit: max_j d_j with one 3-input max (FMNMX3) per column pair instead of
+// a per-column sign mask.  Almost every unit has no candidate at all (max < 0), so the per-column mask
+// (prefilter_unit) is only computed for the few units where some lane's maximum is >= 0.
+__device__ __forceinline__ float prefilter_unit_max(const float4 *__restrict__ cs, const uint32_t (&v)[32],
+                                                    unsigned long long SS, unsigned long long PP)
+{
+    float m = __int_as_float(0xff800000);  // -inf
+#if FOCR_SCALAR_FFMA
+    float S1, S1b, P1, P1b;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(S1), "=f"(S1b) : "l"(SS));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(P1), "=f"(P1b) : "l"(PP));
+#endif
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        const float4 c = cs[j >> 1];
+#if FOCR_SCALAR_FFMA
+        float d0 = __fmaf_rn(c.x, S1, __int2float_rn((int)v[j])), d1 = __fmaf_rn(c.y, S1, __int2float_rn((int)v[j + 1]));
+        d0 = __fmaf_rn(c.z, P1, d0);
+        d1 = __fmaf_rn(c.w, P1, d1);
+#else
+        unsigned long long d = pack2(__int2float_rn((int)v[j]), __int2float_rn((int)v[j + 1]));
+        d = ffma2(pack2(c.x, c.y), SS, d);
+        d = ffma2(pack2(c.z, c.w), PP, d);
+        float d0, d1;
+        asm("mov.b64 {%0,%1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+#endif
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(m), "f"(d0), "f"(d1));
+    }
+    return m;
+}
+
+// the rare path (kept out of line, re-reads the unit from TMEM so nothing has to be passed in memory)
+__device__ __noinline__ void candidates_of_unit(const TcParams &p, const float4 *cst_unit, uint32_t taddr, int col,
+                                                unsigned long long SS, unsigned long long PP, bool valid, int page,
+                                                int gx, int y)
+{
+    uint32_t v[32];
+    tc_ld32(taddr, v);
+    tc_wait_ld32(v);
+    const uint32_t sign = prefilter_unit(cst_unit, v, SS, PP);
+    const uint32_t cand = valid ? ~sign : 0u;
+    uint32_t any = __reduce_or_sync(0xffffffffu, cand);
+    while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
+        const int b = 31 - __clz(any);
+        any &= ~(1u << b);
+        const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;
+        const uint32_t a = tc_ld1(taddr + j);  // re-read that column from TMEM (uniform address)
+        tc_wait_ld();
+        if ((cand >> b) & 1u) push_candidate(p, a, col + j, page, gx, y);
+    }
+}
+
+__device__ __forceinline__ void handle_unit(const TcParams &p, const float4 *cst_unit, uint32_t taddr, int col,
                                             const uint32_t (&v)[32], unsigned long long SS, unsigned long long PP,
                                             bool valid, int page, int gx, int y)
 {
-    const uint32_t sign = prefilter_unit(cst_s + (col >> 1), v, SS, PP);
-    const uint32_t cand = valid ? ~sign : 0u;
-    if (__any_sync(0xffffffffu, cand != 0)) {
-        uint32_t any = __reduce_or_sync(0xffffffffu, cand);
-        while (any) {  // warp-uniform loop over the (few) columns in which some lane has a candidate
-            const int b = 31 - __clz(any);
-            any &= ~(1u << b);
-            const int j = b >= 16 ? 2 * (31 - b) : 2 * (15 - b) + 1;
-            const uint32_t a = tc_ld1(taddr + j);  // re-read that column from TMEM (uniform address)
-            tc_wait_ld();
-            if ((cand >> b) & 1u) push_candidate(p, a, col + j, page, gx, y);
-        }
-    }
+    const float m = prefilter_unit_max(cst_unit, v, SS, PP);
+    if (__any_sync(0xffffffffu, valid && m >= 0.f))
+        candidates_of_unit(p, cst_unit, taddr, col, SS, PP, valid, page, gx, y);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
@@ -361,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
             mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, 1);     // tcgen05.commit
+            mbar_init(a_empty + i, 2);     // one tcgen05.commit per MMA-issuing warp
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
@@ -406,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0 + (size_t)it.ys0 * p.pitch;
             const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
             for (int r = 0; r < n_rows; r++, src += p.pitch) {
-                if (in_group == 0 && !first_round) mbar_wait<200>(raw_empty + rg, rgpar);
+                if (in_group == 0 && !first_round) mbar_wait<20000>(raw_empty + rg, rgpar);
                 if (elect_one()) {
                     mbar_expect_tx(raw_full + rg, row_bytes);
                     tma_bulk_g2s(raw + slot * TC_RAW_BYTES, src, row_bytes, raw_full + rg);
@@ -421,18 +477,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             }
         }
         if (in_group != 0 && elect_one()) mbar_arrive(raw_full + rg);  // the last, partial group
-    } else if (warp == 1) {
-        // ================================================================== MMA issuer
-        // Warp-uniform control flow (the loop state stays in uniform registers, no R2UR / ELECT loops
-        // around every UTCIMMA) and no divisions: a single warp issues all tensor work of the SM, so
-        // its instruction count per tcgen05.mma bounds the kernel once the other roles keep up.
+    } else if (warp == 1 || warp == 2) {
+        // ================================================================== MMA issuers (two warps)
+        // One warp cannot issue fast enough: its serial instruction stream (descriptor arithmetic, R2UR,
+        // UTCIMMA, commits; ~7 cycles per dependent instruction) costs more per output row than the
+        // tensor core needs for the row's MMAs.  Output rows therefore alternate between two issuing
+        // warps (row parity); they touch different accumulators, so their relative order is free.
+        //   * a page-row group goes back to the expansion warps when BOTH issuers have moved past it:
+        //     each commits to a_empty[g] (count 2) once its next output no longer reads group g --
+        //     tcgen05.commit only tracks the MMAs of the committing thread.
+        const uint32_t mw = warp - 1;
         const uint32_t idesc = (2u << 4)                         // D format: S32
                                | (0u << 7) | (0u << 10)          // A, B: unsigned 8-bit
                                | (0u << 15) | (0u << 16)         // A, B: K-major
                                | ((uint32_t)(p.n_mma >> 3) << 17)  // N
                                | ((128u >> 4) << 24);            // M = 128
-        const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp,
-                       nsub = p.nsub;
+        const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp;
         const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4;
         const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
         const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
@@ -440,93 +500,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // SBO = 128 B, version = 1
         const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
         const uint32_t b_lo0 = ((smem_u32(btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+        const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
         mbar_wait(bar_btile, 0);
-        uint32_t s_first = 0;                    // ring slot of the output row's first page row
-        uint32_t rel_in_group = 0, rel_g = 0;    // release bookkeeping: position of s_first inside its group
-        uint32_t new_in_group = 0, new_g = 0, new_par = 0;  // group of the NEXT not-yet-awaited page row
-        uint32_t rows_ready = 0, rows_needed = n_hp;         // page rows known to be expanded / needed by this output
-        uint32_t buf = 0, bpar = 0;
+        uint32_t g_first = 0;                    // global page-row index of the current output row's first row
+        uint32_t s_first = 0;                    // its ring slot (g_first mod ring_n)
+        uint32_t rel_g = 0, rel_rows = TC_G;     // next group to hand back; rel_rows = 4*(groups released + 1)
+        uint32_t new_g = 0, new_par = 0, rows_ready = 0;  // a_full bookkeeping (per warp)
+        uint32_t job = 0, buf = 0, bpar = 0;     // accumulator sequence (all jobs, both warps count them)
         bool first_round = true;
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int n_out_rows = it.ys1 - it.ys0;
-            // Two accumulators are always in flight: consecutive tcgen05.mma into the SAME accumulator
-            // serialise on the accumulate dependency (~100 cycles each, measured), so the K steps of two
-            // independent jobs are interleaved -- the two column halves of one output row when nsub == 2,
-            // else two consecutive output rows.
-            for (int j = 0; j < n_out_rows;) {
-                // pairing two rows needs two free accumulators at once: only worth it when there are >= 4 buffers
-                const bool two_rows = nsub == 1 && nbuf >= 4 && j + 1 < n_out_rows;
-                const uint32_t njobs = nsub == 2 ? 2u : (two_rows ? 2u : 1u);
-                const uint32_t need = rows_needed + (two_rows ? 1u : 0u);
-                while (rows_ready < need) {   // at most once per 4 output rows in steady state
-                    mbar_wait<20>(a_full + new_g, new_par);
-                    rows_ready += TC_G;
-                    if (++new_g == ring_g) new_g = 0, new_par ^= 1;
-                }
-                uint32_t buf1 = buf + 1, bpar1 = bpar;
-                bool first1 = first_round;
-                if (buf1 == nbuf) buf1 = 0, bpar1 ^= 1, first1 = false;
-                if (!first_round) mbar_wait<20>(t_empty + buf, bpar ^ 1);
-                if (njobs == 2 && !first1) mbar_wait<20>(t_empty + buf1, bpar1 ^ 1);
-                tc_fence_after();
-                {
-                    // All lanes run the (warp-uniform) descriptor arithmetic so that it stays on the uniform
-                    // datapath; only the tcgen05 instructions themselves are predicated on the elected lane.
-                    const bool leader = elect_one();
-                    const uint32_t d0 = tmem_base + buf * p.nbs, d1 = tmem_base + buf1 * p.nbs;
-                    uint32_t s0 = s_first, s1 = s_first + (two_rows ? 1u : 0u);
-                    if (s1 >= ring_n) s1 -= ring_n;
-                    uint32_t al0 = a_lo0 + s0 * pitch16, al1 = a_lo0 + s1 * pitch16;
-                    const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
-                    uint32_t bl0 = b_lo0, bl1 = b_lo0 + (nsub == 2 ? (uint32_t)p.n_mma : 0u);  // template n sits n*16 B into a K chunk
-                    for (uint32_t k = 0; k < ksteps; k++) {
-                        if (leader) {
-                            tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | al0, ((uint64_t)desc_hi << 32) | bl0, idesc, k);
-                            if (k + 1 == ksteps) tc_commit(t_full + buf);       // accumulator ready for the epilogue
-                            if (njobs == 2) {
-                                tc_mma_i8(d1, ((uint64_t)desc_hi << 32) | al1, ((uint64_t)desc_hi << 32) | bl1, idesc, k);
-                                if (k + 1 == ksteps) tc_commit(t_full + buf1);
-                            }
-                        }
-                        al0 += a_inc;
-                        if (al0 >= a_end) al0 -= a_wrap;
-                        al1 += a_inc;
-                        if (al1 >= a_end) al1 -= a_wrap;
-                        bl0 += 2 * b_lbo16;
-                        bl1 += 2 * b_lbo16;
-                    }
-                }
-                __syncwarp();
-                for (uint32_t q2 = 0; q2 < njobs; q2++)
-                    if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
-                // released page rows: a whole group is handed back to the expansion warps at once
-                const int rows_done = two_rows ? 2 : 1;
-                for (int q2 = 0; q2 < rows_done; q2++) {
-                    if (++rel_in_group == TC_G) {
+            for (int j = 0; j < n_out_rows; j++, job++) {
+                if ((job & 1u) == mw) {
+                    // hand back every group that lies entirely below this output's first page row
+                    while (rel_rows <= g_first) {
                         if (elect_one()) tc_commit(a_empty + rel_g);
                         __syncwarp();
-                        rel_in_group = 0;
+                        rel_rows += TC_G;
                         if (++rel_g == ring_g) rel_g = 0;
                     }
-                    if (++s_first == ring_n) s_first = 0;
-                    rows_needed++;
-                }
-                j += rows_done;
-            }
-            // the last n_hp-1 rows of the item are never the first row of an output: release them too
-            for (uint32_t r = 0; r + 1 < n_hp; r++) {
-                if (++rel_in_group == TC_G) {
-                    if (elect_one()) tc_commit(a_empty + rel_g);
+                    while (rows_ready < g_first + n_hp) {   // page rows this output needs
+                        mbar_wait<20000>(a_full + new_g, new_par);
+                        rows_ready += TC_G;
+                        if (++new_g == ring_g) new_g = 0, new_par ^= 1;
+                    }
+                    if (!first_round) mbar_wait<20000>(t_empty + buf, bpar ^ 1);
+                    tc_fence_after();
+                    {
+                        const bool leader = elect_one();
+                        const uint32_t d0 = tmem_base + buf * p.nbs;
+                        uint32_t al0 = a_lo0 + s_first * pitch16, bl0 = b_lo0;
+                        for (uint32_t k = 0; k < ksteps; k++) {
+                            if (leader) {
+                                tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | al0, ((uint64_t)desc_hi << 32) | bl0, idesc, k);
+                                if (k + 1 == ksteps) tc_commit(t_full + buf);   // accumulator ready for the epilogue
+                            }
+                            al0 += a_inc;
+                            if (al0 >= a_end) al0 -= a_wrap;
+                            bl0 += 2 * b_lbo16;
+                        }
+                    }
                     __syncwarp();
-                    rel_in_group = 0;
-                    if (++rel_g == ring_g) rel_g = 0;
                 }
+                if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
+                g_first++;
                 if (++s_first == ring_n) s_first = 0;
-                rows_needed++;
             }
+            // the item's last n_hp-1 page rows are not the first row of any output
+            g_first += n_hp - 1;
+            s_first += n_hp - 1;
+            while (s_first >= ring_n) s_first -= ring_n;
         }
-        (void)new_in_group;
     } else if (warp >= 4 && warp < 8) {
         // ================================================================== Toeplitz expansion
         // one warp per page row, four rows (one group) in flight per handshake
@@ -536,8 +561,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         uint32_t rg = 0, rgpar = 0, ag = 0, agpar = 1;
         bool first_round = true;
         for (uint32_t g0 = 0; g0 < total_rows; g0 += TC_G) {
-            mbar_wait<100>(raw_full + rg, rgpar);
-            if (!first_round) mbar_wait<100>(a_empty + ag, agpar);
+            mbar_wait<20000>(raw_full + rg, rgpar);
+            if (!first_round) mbar_wait<20000>(a_empty + ag, agpar);
             if (g0 + w < total_rows) {
                 const uint32_t *rw = (const uint32_t *)(raw + (rg * TC_G + w) * TC_RAW_BYTES);
                 const uint32_t s = ag * TC_G + w;
@@ -618,16 +643,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 const float Pv = valid ? P : 0.f;
                 const unsigned long long SS = pack2(S, S), PP = pack2(Pv, Pv);
                 for (int sub = 0; sub < nsub; sub++) {
-                    mbar_wait(t_full + buf, bpar);
+                    mbar_wait<20000>(t_full + buf, bpar);
                     tc_fence_after();
                     const uint32_t tb = tlane + buf * p.nbs;
                     const int cbase = sub * p.n_mma;
                     if (p.dbg_mode != 1) {
                         for (int u = ufirst; u < nunits; u += TC_EPI_GROUPS) {
                             uint32_t v[32];
-                            tc_ld32(tb + u * 32, v);
-                            tc_wait_ld32(v);
-                            handle_unit(p, cst_s, tb + u * 32, cbase + u * 32, v, SS, PP, valid, it.page, gx, y);
+                            if (p.dbg_mode != 4) {
+                                tc_ld32(tb + u * 32, v);
+                                tc_wait_ld32(v);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; i++) v[i] = (uint32_t)(u + i) * 3u;  // timing experiment: math without TMEM reads
+                            }
+                            if (p.dbg_mode == 3) {  // timing experiment: TMEM reads without math
+                                if (v[5] == 0x7fffffffu && v[17] == 0x12345u) push_candidate(p, v[0], 0, 0, 0, 0);
+                                continue;
+                            }
+                            handle_unit(p, cst_s + (((sub * nunits + u) * 32) >> 1), tb + u * 32, cbase + u * 32, v, SS, PP, valid,
+                                        it.page, gx, y);
                         }
                     }
                     if (p.dbg_acc && p.dbg_col >= cbase && p.dbg_col < cbase + p.n_mma && grp == 0) {
@@ -798,7 +833,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.nb = tc.nb;
     // one MMA covers all nb columns: a tcgen05.mma carries ~100 cycles of fixed cost (measured), so fewer,
     // wider instructions win over finer TMEM buffering; FOCR_TC_NSUB2 re-enables the split for experiments
-    p.nsub = (tc.nb > 128 && getenv("FOCR_TC_NSUB2")) ? 2 : 1;
+    p.nsub = 1;
     p.n_mma = tc.nb / p.nsub;
     p.nunits = (p.n_mma + 31) / 32;
     p.nbs = (p.n_mma + 31) & ~31;
@@ -837,9 +872,12 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.dbg_col = dbg_acc ? dbg_pos % (int)tc.nb : -1;
     for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
-        for (int col = 0; col < 256; col++) {
+        // table index = (sub * nunits + unit) * 32 + j  (each sub-block padded to whole 32-column units)
+        for (int idx = 0; idx < 256; idx++) {
             float2 c = make_float2(-INFINITY, 0.f);  // padding: d = -inf -> never a candidate
-            if (col < (int)tc.nb) {
+            const int sub = idx / (p.nunits * 32), within = idx % (p.nunits * 32);
+            const int col = sub * p.n_mma + within;
+            if (sub < p.nsub && within < p.n_mma && col < (int)tc.nb) {
                 const float2 s = cst[(size_t)blk * tc.nb + col];
                 if (std::isfinite(s.x)) {
                     const float aa = thr * s.x;  // a = thr * norm_n
@@ -847,7 +885,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
                     c.y = -(s.y * dn);
                 }
             }
-            p.cst[col] = c;
+            p.cst[idx] = c;
         }
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
         p.col_base = blk * tc.nb;
