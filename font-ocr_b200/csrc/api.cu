@@ -79,7 +79,7 @@ struct DevBuf {
 };
 
 struct Slot {  // everything one in-flight chunk of pages needs
-    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, cands, sel, ycut, selcount, flags, out, counts, acc;
+    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
     unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     uint32_t hits_per_page = 0;
@@ -92,6 +92,7 @@ struct focr_ctx {
     uint64_t launches = 0;
     Slot slot[2];
     uint32_t hits_per_page = 2u << 20;
+    uint32_t cand_per_warp = 16384;  // capacity of each epilogue warp's private candidate list (grows on overflow)
     int sm_count = 148;
     TcWorkspace tc;
     // per-stage profiling (focr_ctx_profile)
@@ -174,7 +175,7 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slot) {
-        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.cands, &s.sel, &s.ycut,
+        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.cands, &s.candcnt, &s.sel, &s.ycut,
                           &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
             b->release();
         if (s.flags_host) cudaFreeHost(s.flags_host);
@@ -385,7 +386,11 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     CU(s.hits.ensure(hit_cap * sizeof(Hit)));
     bool any_tc = false;
     for (auto &ch : b->classes) any_tc |= use_tc(c, ch);
-    if (any_tc) CU(s.cands.ensure(hit_cap * sizeof(Hit)));
+    const size_t n_lists = (size_t)c->sm_count * 8;
+    if (any_tc) {
+        CU(s.cands.ensure(n_lists * c->cand_per_warp * sizeof(Hit)));
+        CU(s.candcnt.ensure(n_lists * 4));
+    }
     CU(s.sel.ensure(PT * g.sel_cap * 8));
     CU(s.ycut.ensure(PT * 4));
     CU(s.selcount.ensure(PT * 4));
@@ -456,11 +461,11 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.thr_f = threshold;
         a.sink = sink;
         a.cands = s.cands.as<Hit>();
-        a.cand_cap = sink.hit_cap;
-        a.cand_count = s.flags.as<unsigned int>() + 2;
+        a.cand_cap = c->cand_per_warp;
+        a.cand_count = s.candcnt.as<unsigned int>();
         a.cand_max = s.flags.as<unsigned int>() + 3;
         a.acc_out = nullptr;
-        if (tc) CU(cudaMemsetAsync(a.cand_count, 0, 4, st));
+        if (tc) CU(cudaMemsetAsync(a.cand_count, 0, n_lists * 4, st));
         int nl = 0;
         {
             StageTimer tm(c, FOCR_STAGE_SCAN);
@@ -502,8 +507,15 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
 // after the stream has been synchronised: did the chunk's hit list overflow?
 static bool chunk_overflowed(focr_ctx *c, Slot &s, uint32_t nB)
 {
+    if (getenv("FOCR_DEBUG_COUNTS"))
+        fprintf(stderr, "[focr] chunk of %u pages: hits %u, longest overflowing candidate list %u (cap %u)\n", nB,
+                s.flags_host[0], s.flags_host[3], c->cand_per_warp);
+    if (s.flags_host[3] > c->cand_per_warp) {  // a warp's private candidate list overflowed
+        c->cand_per_warp = (uint32_t)std::min<size_t>((size_t)s.flags_host[3] + s.flags_host[3] / 2, 1u << 24);
+        return true;
+    }
     const size_t cap = (size_t)s.hits_per_page * nB;
-    const size_t seen = std::max(s.flags_host[0], s.flags_host[3]);  // hits and prefilter candidates share the capacity
+    const size_t seen = s.flags_host[0];
     if (seen > cap) {
         const size_t need = (seen + nB - 1) / nB;
         c->hits_per_page = (uint32_t)std::min<size_t>(need + need / 4 + 1024, 0x7FFFFFFFu);
@@ -760,9 +772,11 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     a.sink.rowcount = s.rowcount.as<unsigned int>();
     a.sink.T = b->T;
     a.sink.r_h = r_h;
-    a.cands = nullptr;
-    a.cand_cap = 0;
-    a.cand_count = s.flags.as<unsigned int>() + 2;
+    CU(s.cands.ensure((size_t)c->sm_count * 8 * 16 * sizeof(Hit)));
+    CU(s.candcnt.ensure((size_t)c->sm_count * 8 * 4));
+    a.cands = s.cands.as<Hit>();
+    a.cand_cap = 16;
+    a.cand_count = s.candcnt.as<unsigned int>();
     a.cand_max = s.flags.as<unsigned int>() + 3;
     a.acc_out = s.acc.as<uint32_t>();
     int nl = 0;

@@ -15,8 +15,7 @@ struct TcClass {
     uint32_t kchunks = 0;   // 16-byte K chunks per template = n_h * np/16
     uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
     uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]
-    float2 *consts = nullptr;     // (unused on the device: the constants travel in the kernel parameter bank)
-    void *consts_host = nullptr;  // std::vector<float2>* [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding/constant templates
+    float2 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
     uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
 };
 

@@ -34,3 +34,12 @@ print("lists equal:", m0.tobytes() == m1.tobytes())
 if not np.array_equal(c0, c1):
     bad = np.nonzero(c0[0] != c1[0])[0]
     print("templates with different counts:", bad[:20], c0[0][bad[:20]], c1[0][bad[:20]])
+if not np.array_equal(c0, c1) or m0.tobytes() != m1.tobytes():
+    t = int(np.nonzero(c0[0] != c1[0])[0][0]) if not np.array_equal(c0, c1) else 0
+    a, b = m0[0, t, :c0[0, t]], m1[0, t, :c1[0, t]]
+    print("template", t, "simt", len(a), "tc", len(b))
+    sa = {(int(r["x"]), int(r["y"])) for r in a}
+    extra = [(int(r["x"]), int(r["y"]), float(r["similarity"])) for r in b if (int(r["x"]), int(r["y"])) not in sa]
+    print("extra in tc (first 12):", extra[:12])
+    keys = [(int(r["y"]), int(r["x"])) for r in b]
+    print("duplicates in tc:", len(keys) - len(set(keys)))
