@@ -42,11 +42,12 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    dg = _digest()
+    dg = _digest() + ("+exp" if os.environ.get("FOCR_TC_EXPERIMENTS") else "")
     if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read() == dg:
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = ["-DFOCR_TC_EXPERIMENTS"] if os.environ.get("FOCR_TC_EXPERIMENTS") else []  # tools/tc_trace.py, tools/tc_modes.py
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -80,7 +80,8 @@ struct DevBuf {
 
 struct Slot {  // everything one in-flight chunk of pages needs
     DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
-    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark
+    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark,
+                                         // [4..9] scan_tc watchdog (raised, tag, info, CTA, warp, parity)
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     uint32_t hits_per_page = 0;
 };
@@ -119,6 +120,13 @@ struct StageTimer {  // RAII: events around one stage when profiling is on
     {
         if (a) { cudaEvent_t b = c->get_event(); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, stage, launches}); }
     }
+};
+
+struct ExactStage : TcHook {  // the exact pass as its own profiling stage (inside FOCR_STAGE_SCAN)
+    focr_ctx *c; StageTimer *t = nullptr;
+    explicit ExactStage(focr_ctx *c_) : c(c_) {}
+    void exact_begin() override { t = new StageTimer(c, FOCR_STAGE_EXACT); }
+    void exact_end() override { delete t; t = nullptr; }
 };
 
 struct ClassHost {
@@ -386,7 +394,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     CU(s.hits.ensure(hit_cap * sizeof(Hit)));
     bool any_tc = false;
     for (auto &ch : b->classes) any_tc |= use_tc(c, ch);
-    const size_t n_lists = (size_t)c->sm_count * 8;
+    const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
     if (any_tc) {
         CU(s.cands.ensure(n_lists * c->cand_per_warp * sizeof(Hit)));
         CU(s.candcnt.ensure(n_lists * 4));
@@ -469,8 +477,10 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         int nl = 0;
         {
             StageTimer tm(c, FOCR_STAGE_SCAN);
-            if (tc)
-                CU(launch_scan_tc(c->tc, ch.tc, a, nB, c->sm_count, st, &nl));
+            if (tc) {
+                ExactStage hook(c);
+                CU(launch_scan_tc(c->tc, ch.tc, a, nB, c->sm_count, st, &nl, nullptr, -1, &hook));
+            }
             else
                 CU(launch_scan_simt(a, nB, st, &nl));
             tm.launches = nl;
@@ -500,11 +510,20 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         CU(launch_finalize(f, st, &nl));
     }
     c->launches += nl;
-    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 64, cudaMemcpyDeviceToHost, st));
     return FOCR_OK;
 }
 
 // after the stream has been synchronised: did the chunk's hit list overflow?
+// after the stream has been synchronised: did a wait inside the tcgen05 kernel give up (protocol bug)?
+static int chunk_watchdog(Slot &s)
+{
+    if (!s.flags_host[4]) return FOCR_OK;
+    return fail(FOCR_ERR_CUDA, "internal: scan_tc pipeline stalled (wait tag " + std::to_string(s.flags_host[5]) + ", info " +
+                                   std::to_string(s.flags_host[6]) + ", CTA " + std::to_string(s.flags_host[7]) + ", warp " +
+                                   std::to_string(s.flags_host[8]) + ", parity " + std::to_string(s.flags_host[9]) + ")");
+}
+
 static bool chunk_overflowed(focr_ctx *c, Slot &s, uint32_t nB)
 {
     if (getenv("FOCR_DEBUG_COUNTS"))
@@ -556,6 +575,7 @@ extern "C" int focr_ncc_scan_device(focr_ctx *c, const focr_bank *b, const uint8
             if (rc) return rc;
             CU(cudaStreamSynchronize(c->stream));
             if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+            if (int wrc = chunk_watchdog(s)) return wrc;
             redo = chunk_overflowed(c, s, nB);
         }
         if (!redo) return FOCR_OK;
@@ -586,6 +606,7 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             if (ci >= 2) {  // the slot's previous chunk must be fully drained before its buffers are reused
                 CU(cudaEventSynchronize(s.ev_d2h));
                 if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+            if (int wrc = chunk_watchdog(s)) return wrc;
                 if (chunk_overflowed(c, s, std::min(B, n_pages - (p0 - 2 * B)))) {
                     redo = true;
                     break;
@@ -623,6 +644,7 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             for (uint32_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; k++) {
                 Slot &s = c->slot[k & 1];
                 if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+            if (int wrc = chunk_watchdog(s)) return wrc;
                 const uint32_t nB = std::min(B, n_pages - k * B);
                 if (chunk_overflowed(c, s, nB)) redo = true;
             }
@@ -772,8 +794,8 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     a.sink.rowcount = s.rowcount.as<unsigned int>();
     a.sink.T = b->T;
     a.sink.r_h = r_h;
-    CU(s.cands.ensure((size_t)c->sm_count * 8 * 16 * sizeof(Hit)));
-    CU(s.candcnt.ensure((size_t)c->sm_count * 8 * 4));
+    CU(s.cands.ensure((size_t)c->sm_count * TC_LISTS_PER_CTA * 16 * sizeof(Hit)));
+    CU(s.candcnt.ensure((size_t)c->sm_count * TC_LISTS_PER_CTA * 4));
     a.cands = s.cands.as<Hit>();
     a.cand_cap = 16;
     a.cand_count = s.candcnt.as<unsigned int>();

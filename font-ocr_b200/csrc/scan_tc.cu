@@ -16,30 +16,36 @@
 //    are 1 B apart, so each page row is expanded ONCE into a 128 x 16 B block in shared memory and
 //    reused by all n_h vertical taps and all N templates (descriptor LBO points at ring slots y+2k, y+2k+1).
 //    Raw page rows arrive by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 4 rows per barrier.
-//  * 7 x tcgen05.mma kind::i8 per row accumulate acc EXACTLY into a TMEM accumulator that was pre-biased
-//    with 0x4B000000: the s32 bits 0x4B000000 + acc ARE the fp32 number 2^23 + acc (acc < 2^23; larger acc
-//    only over-estimates, see below).
-//  * 1 x tcgen05.mma kind::f16 (K = 16, fp32 accumulate) then adds -(b_t*S_m + a_t*P_m) to the SAME TMEM
-//    columns, read as fp32: A2[m] = {S_hi, S_hi, S_lo, P_1, P_1, P_2, V, K} and
-//    B2[t] = -{b_1, b_2, b_1, a_1, a_2, a_1, BIG, pad} are fp16 hi/lo splits (error < 8 in units of acc);
-//    V = BIG marks windows that can never hit (constant / out of range), pad = BIG marks padding columns.
-//    The accumulator now holds 2^23 + d (+- a few ulp): the epilogue is ONE 3-input max per column pair
-//    and a compare against 2^23 - margin -- no conversion, no FMA, no per-column constants.
+//  * 1 x tcgen05.mma kind::f16 (K = 16, fp32 result, accumulate OFF) first writes F = C0 - (b_t*S_m + a_t*P_m)
+//    into the accumulator: A2[m] = {S_hi, S_hi, S_lo, P_1, P_1, P_2, V, 2^15} and
+//    B2[t] = {-b_1, -b_2, -b_1, -a_1, -a_2, -a_1, -BIG, 510 | -BIG} are fp16 hi/lo splits (error < 8 in units of
+//    acc); C0 = 2^15 * 510 = 2^24 - 2^16.  V = BIG marks windows that can never hit (constant / out of range),
+//    the last B2 entry is -BIG for padding columns.  F lies in [2^23, 2^24) where fp32 has ulp 1, so its BITS are
+//    0x4B000000 + (F - 2^23): an integer that is linear in F.
+//  * 7 x tcgen05.mma kind::i8 then accumulate acc EXACTLY, as s32, onto those bits: the cell now holds the bits
+//    of the fp32 number C0 + d (+- a few ulp; if the sum leaves the binade upwards it only over-estimates, fp32
+//    bit patterns are monotonic).  Nothing has to be written back before the next row: the epilogue is ONE
+//    3-input max per column pair and a compare against C0 - margin -- no conversion, no FMA, no per-column
+//    constants, no tcgen05.st.  Windows whose b_max*S + a_max*P would push F below 2^23 (finer ulp, the bits
+//    stop being linear and would UNDER-estimate) are flagged V = -BIG instead: they always survive the screen.
 //  * survivors (d >= -margin; a few per thousand outputs) go to a candidate list; cand_exact_kernel
 //    recomputes acc with integer arithmetic and replays the reference's f64 normalisation operation for
 //    operation, so decisions and f32 scores are bit-identical to the CPU.  Nothing can be missed: every
 //    approximation errs towards MORE candidates.
 //
-// Warp roles (640 threads, one persistent CTA per SM over (page, x-strip, y-segment) items):
-//   warp 0     TMA producer of raw page rows         warps 1-2   MMA issuers (alternate output rows)
-//   warp 3     idle (TMEM alloc)                     warps 4-7   Toeplitz expansion (one warp per row)
-//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-19 epilogue (2 per TMEM lane quarter)
+// Warp roles (one persistent CTA per SM over (page, x-strip, y-segment) items):
+//   warp 0     TMA producer of raw page rows         warps 1-2   MMA issuers (one elected thread each, alternate rows)
+//   warp 3     TMEM alloc, otherwise idle            warps 4-7   Toeplitz expansion (one warp per row)
+//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-   epilogue (TC_EPI_GROUPS per TMEM lane quarter)
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "scan_tc.cuh"
@@ -48,7 +54,10 @@ namespace cg = cooperative_groups;
 
 namespace focr {
 
-constexpr int TC_THREADS = 640;
+constexpr int TC_EPI_GROUPS = 4;      // epilogue warps per TMEM lane quarter
+constexpr int TC_THREADS = 384 + 128 * TC_EPI_GROUPS;
+static_assert(TC_LISTS_PER_CTA == 4 * TC_EPI_GROUPS, "scan_tc.cuh: candidate lists per CTA = epilogue warps");
+static_assert(TC_EPI_GROUPS == 4, "the epilogue is written for 2 teams x 2 warps per lane quarter");
 constexpr int TC_G = 4;               // rows per pipeline group: one mbarrier handshake per 4 rows
 constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
 constexpr int TC_RAW_SLOTS = TC_RAW_GROUPS * TC_G;
@@ -58,9 +67,16 @@ constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: 4 groups x 4 output rows x 2 KB
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
 constexpr int TC_YSEG = 128;          // output rows per work item
-constexpr int TC_EPI_GROUPS = 2;      // epilogue warps per TMEM lane quarter
+// setmaxnreg budget (the kernel is compiled for 72 registers x 896 threads): warps 0-3 (TMA producer, MMA issuer) keep
+// 64, Toeplitz warps 40, A2 warps 48, epilogue warps 88: 128 x (64 + 40 + 48) + 512 x 88 = 64512 (an exact fit of
+// 65536 made setmaxnreg.inc wait for ever)
+constexpr int TC_REGS_TOEPLITZ = 40;
+constexpr int TC_REGS_A2 = 48;
+constexpr int TC_REGS_EPILOGUE = 88;
+constexpr int TC_REGS_ISSUE = 64;
 constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
-constexpr uint32_t TC_BIAS = 0x4B000000u;        // fp32 2^23
+constexpr float TC_C0 = 16711680.f;               // 2^15 * 510 = 2^24 - 2^16: the constant term of the fp16 MMA
+constexpr float TC_KCAP = 8323072.f - 8192.f;     // C0 - 2^23 minus slack: largest b*S + a*P that keeps F in [2^23, 2^24)
 constexpr float TC_BIG = 60000.f;                 // fp16-representable "never" marker (BIG*BIG = 3.6e9 >> any acc)
 constexpr float TC_MARGIN = 256.f;                // absolute slack of the tensor-core normalisation, in units of acc (error budget < 60)
 
@@ -83,17 +99,25 @@ struct TcParams {
     uint32_t btile_bytes;
     const float2 *colconst;   // [nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
     float thr;
+    float bmax, amax;         // max over this launch's columns of s_n/n and max(thr*norm_n, 0)
     uint32_t col_base;        // this launch's first column within the class (N-block * nb)
     const uint32_t *sp;
     const float *pf;
     int spitch;
     size_t plane_page_stride;
-    Hit *cands;               // candidate lists, one PRIVATE list per epilogue warp: [grid*8][cand_cap] {class column, y<<16|x, -, page}
+    Hit *cands;               // candidate lists, one PRIVATE list per epilogue warp: [grid*TC_LISTS_PER_CTA][cand_cap] {class column, y<<16|x, -, page}
     uint32_t cand_cap;        // entries per warp list
-    unsigned int *cand_count; // [grid*8] entries each warp produced (may exceed cand_cap -> the host grows the lists and retries)
+    unsigned int *cand_count; // [grid*TC_LISTS_PER_CTA] entries each warp produced (may exceed cand_cap -> the host grows the lists and retries)
     int n_pages, n_xstrips, n_ysegs;
-    int dbg_mode;       // timing experiments only (env FOCR_TC_DBG): 1 = epilogue skips the TMEM reads
-    uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x]; disables the correction MMA
+    unsigned int *wd;   // watchdog words (see mbar_wait): [0] raised, [1] tag, [2] info, [3] CTA, [4] warp, [5] parity
+    long long *trace;   // timing experiments (env FOCR_TC_TRACE=file): CTA 0's roles add up the cycles they spend in each
+                        // wait / phase, [64] (tools/tc_trace.py names the slots)
+    int issuers;        // MMA-issuing threads: 2 (default) or 1 (env FOCR_TC_ISSUERS, experiments)
+    int spin;           // bit 0: epilogue polls t_full, bit 1: MMA warps poll t_empty (env FOCR_TC_SPIN, default 3)
+    int dbg_mode;       // timing experiments only (env FOCR_TC_DBG, a bit mask; results are wrong when non-zero):
+                        // 1 epilogue skips the TMEM reads, 2 epilogue loads but does not screen, 4 no MMAs are issued,
+                        // 8 A2 rows skip their global loads, 16 no Toeplitz expansion, 32 A2 rows skip their stores
+    uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x]; disables the fp16 MMA
     int dbg_col;
 };
 
@@ -126,19 +150,63 @@ __device__ __forceinline__ bool elect_one()
         : "=r"(pred));
     return pred != 0;
 }
+__device__ uint4 *g_wdlog = nullptr;
+__device__ uint32_t g_wdprog[32];
+
 // Wait for a phase of an mbarrier with a suspend-time hint: the hardware parks the thread (few issue
 // slots taken from busy warps) and wakes it as soon as the phase completes.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+// Watchdog: a wait that has timed out ~8000 times (>= 0.15 s) records who is stuck (wd[1..4] = tag, info, CTA,
+// warp) and raises wd[0]; every waiting thread that sees wd[0] gives up, so a protocol bug ends the kernel with an
+// error the host reports instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
+                                          uint32_t info = 0, volatile uint32_t *prog = nullptr)
 {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
+    uint32_t done, tries = 0;
+    for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+        if (done) return;
+        if (wd && (++tries & 63u) == 0) {
+            if (tries == 4096u && prog && atomicCAS(wd + 6, 0u, 1u) == 0u) {  // first long wait anywhere: snapshot of the CTA's progress
+                for (int i = 0; i < 32; i++) g_wdprog[i] = prog[i];
+                wd[7] = blockIdx.x, wd[8] = threadIdx.x >> 5, wd[9] = tag;
+                __threadfence();
+            }
+            if (tries == 8192u && g_wdlog) {  // debugging aid (env FOCR_TC_WDLOG): what this warp has been stuck on
+                uint4 *slot = g_wdlog + (size_t)blockIdx.x * 32 + (threadIdx.x >> 5);
+                if (slot->x == 0) *slot = make_uint4(tag, info, parity, addr);
+            }
+            // give up after ~0.3 s, or ~0.15 s when another wait has already given up
+            if (tries >= 16384u || (tries >= 8192u && *(volatile unsigned int *)wd != 0)) {
+                if (atomicCAS(wd, 0u, 1u) == 0u) {
+                    wd[1] = tag, wd[2] = info, wd[3] = blockIdx.x, wd[4] = threadIdx.x >> 5;
+                    wd[5] = parity;
+                    __threadfence();
+                }
+                return;
+            }
+        }
+    }
+}
+// Latency-critical waits (accumulator hand-offs): plain polling, no suspend -- the wake-up of a parked thread
+// costs more than the whole epilogue of a row.
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
             : "memory");
     } while (!done);
 }
@@ -158,21 +226,33 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-    // always accumulates: the accumulator carries the 0x4B000000 bias
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+// guarded variant for unrolled issue sequences: nothing is issued when guard == 0
+__device__ __forceinline__ void tc_mma_i8_if(uint32_t guard, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(guard)
+        : "memory");
+}
+// D = A*B (accumulate off): the fp16 MMA opens every output row and overwrites the previous row's result
+__device__ __forceinline__ void tc_mma_f16_overwrite(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, 1, 0;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc)
         : "memory");
@@ -198,16 +278,6 @@ __device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
                    "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
 }
-// write the bias back into 32 accumulator columns of this warp's lane quarter
-__device__ __forceinline__ void tc_st32_const(uint32_t taddr, uint32_t c)
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr),
-        "r"(c)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
 {
     uint32_t v;
@@ -215,6 +285,38 @@ __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
     return v;
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Experiment hooks (role time budget, FOCR_TC_DBG modes, progress words) cost instructions in loops whose speed is set
+// by the instruction count of ONE thread, so they are compiled in only with -DFOCR_TC_EXPERIMENTS.
+#ifdef FOCR_TC_EXPERIMENTS
+constexpr bool TC_EXP = true;
+#else
+constexpr bool TC_EXP = false;
+#endif
+#define TC_PROG(slot, value)                  \
+    do {                                      \
+        if (TC_EXP) prog_[(slot)] = (value);  \
+    } while (0)
+
+// role time budget (timing experiments): TT(slot, stmt) runs stmt and, when tracing, adds its cycles to a counter
+#define TT(k, ...)                                  \
+    do {                                            \
+        if (tron) {                                 \
+            const long long t0_ = clock64();        \
+            __VA_ARGS__;                            \
+            tacc[k] += clock64() - t0_;             \
+        } else {                                    \
+            __VA_ARGS__;                            \
+        }                                           \
+    } while (0)
+#define TT_BEGIN() const bool tron = TC_EXP && p.trace != nullptr && blockIdx.x == 0; long long tacc[6] = {0, 0, 0, 0, 0, 0}; const long long tstart_ = tron ? clock64() : 0
+#define TT_END(base)                                                         \
+    do {                                                                     \
+        if (tron) {                                                          \
+            p.trace[(base)] = clock64() - tstart_;                           \
+            for (int i_ = 0; i_ < 6; i_++) p.trace[(base) + 1 + i_] = tacc[i_]; \
+        }                                                                    \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------------- work items
 struct Item {
@@ -261,16 +363,150 @@ __device__ __forceinline__ void append_candidates(Hit *list, uint32_t cap, uint3
     }
 }
 
+// ---------------------------------------------------------------------------------------------- MMA issuers
+struct TcSmem {
+    uint8_t *btile, *ring, *a2ring, *b2tile;
+    uint64_t *bar_btile, *a_full, *a_empty, *a2_full, *a2_empty, *t_full, *t_empty;
+    volatile uint32_t *prog;
+};
+
+// Two issuing threads (one elected lane of warp 1 and of warp 2): thread `mw` owns the output rows whose global
+// index has parity mw.  A single thread's dependent instruction stream (waits, descriptor arithmetic, R2UR,
+// UTCIMMA, commits) runs at ~6 cycles per instruction and cannot feed the tensor pipe alone; two can, and they
+// touch different accumulators, so their relative order is free.  With two accumulators thread mw, accumulator mw
+// and epilogue team mw form one independent pipeline.  A ring group goes back to its producer when BOTH threads
+// have moved past it: each commits to the group's "empty" barrier (count 2) once its next own output no longer
+// reads the group -- tcgen05.commit only tracks the MMAs of the committing thread.
+// KS = K steps per output row as a compile-time constant (0: generic loop): the issue sequence is straight-line
+// code, and because the ring stores its first n_hp-1 slots twice, every descriptor of a row is the first one plus
+// a constant.
+template <int KS>
+__device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t mw)
+{
+    const uint32_t idesc8 = (2u << 4)                          // D format: S32
+                            | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
+                            | (0u << 15) | (0u << 16)          // A, B: K-major
+                            | ((uint32_t)(p.nb >> 3) << 17)    // N
+                            | ((128u >> 4) << 24);             // M = 128
+    const uint32_t idesc16 = (1u << 4)                         // D format: F32 (same TMEM columns, read as fp32)
+                             | (0u << 7) | (0u << 10)          // A, B: F16
+                             | ((uint32_t)(p.nb >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs;
+    const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4, b_inc = 2 * b_lbo16;
+    const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
+    const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
+    const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
+    const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version = 1
+    const uint32_t a_lo0 = ((smem_u32(sm.ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
+    const uint32_t b_lo0 = ((smem_u32(sm.btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+    const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
+    const uint32_t a2_addr16 = (smem_u32(sm.a2ring) & 0x3FFFFu) >> 4, a2_wrap16 = TC_A2_GROUPS * TC_G * (2048u >> 4);
+    const uint32_t a2_end16 = a2_addr16 + a2_wrap16;
+    const uint32_t b2_lo = ((smem_u32(sm.b2tile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+    const bool corr = p.dbg_acc == nullptr;
+    const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : 1u;
+    uint64_t *const a_full = sm.a_full, *const a_empty = sm.a_empty, *const a2_full = sm.a2_full, *const a2_empty = sm.a2_empty,
+                    *const t_full = sm.t_full, *const t_empty = sm.t_empty;
+    volatile uint32_t *const prog_ = sm.prog;
+    mbar_wait(sm.bar_btile, 0, p.wd, 10 + mw, 0);
+    TT_BEGIN();
+    // item-level state (both threads walk all items)
+    uint32_t o_item = 0;                     // global output-row index of the item's first row
+    uint32_t g_item = 0;                     // global page-row index of the item's first row
+    uint32_t a_item = a_lo0;                 // A descriptor (low word) of that row's ring slot
+    // own-row state
+    uint32_t rel_g = 0, rel_rows = TC_G;     // page-row groups: next to hand back / rows covered once it is
+    uint32_t new_g = 0, new_par = 0, rows_ready = 0;
+    uint32_t rel2_g = 0, rel2_rows = TC_G, new2_g = 0, new2_par = 0, rows2_ready = 0;
+    const uint32_t step = p.issuers;         // own rows are `step` apart
+    uint32_t buf = mw, bpar = 0, d0 = mw * nbs;   // accumulator of the next own row (row index mod nbuf), its phase, its TMEM column
+    bool first_round = true;
+    uint32_t o_slot16 = a2_addr16 + mw * (2048u >> 4);   // A2 ring slot address (>> 4) of the next own row
+    Item it;
+    for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
+        const uint32_t n_out_rows = it.ys1 - it.ys0;
+        const uint32_t j0 = step == 2 ? (mw - o_item) & 1u : 0u;   // first own row of the item
+        uint32_t a_first = a_item + j0 * pitch16;        // (a_item < a_end, one slot more never needs two wraps)
+        if (a_first >= a_end) a_first -= a_wrap;
+        for (uint32_t j = j0; j < n_out_rows; j += step) {
+            const uint32_t o = o_item + j, g_first = g_item + j;
+            TC_PROG(1 + mw, (1u << 24) | o);
+            // operands: page rows g_first .. g_first+n_hp-1 and the A2 row of this output
+            while (rows_ready < g_first + n_hp) {
+                TT(0, mbar_wait(a_full + new_g, new_par, p.wd, 12 + mw, o, sm.prog));
+                rows_ready += TC_G;
+                if (++new_g == ring_g) new_g = 0, new_par ^= 1;
+            }
+            while (corr && rows2_ready <= o) {
+                TT(1, mbar_wait(a2_full + new2_g, new2_par, p.wd, 14 + mw, o, sm.prog));
+                rows2_ready += TC_G;
+                if (++new2_g == TC_A2_GROUPS) new2_g = 0, new2_par ^= 1;
+            }
+            TC_PROG(1 + mw, (2u << 24) | o);
+            if (!first_round) TT(2, mbar_wait(t_empty + buf, bpar ^ 1, p.wd, 16 + mw, o, sm.prog));
+            TC_PROG(1 + mw, (3u << 24) | o);
+            tc_fence_after();
+            const long long ti_ = tron ? clock64() : 0;
+            // F = A2 . B2^T in fp32 (accumulate off).  K = 16 fp16 = two 16-byte chunks: both read the row's
+            // statistics (LBO = 0) and the second chunk of B2 is all zeros.
+            if (corr && mma_on) tc_mma_f16_overwrite(d0, desc_hi | o_slot16, desc_hi | b2_lo, idesc16);
+            // K steps: consecutive ring slots (no wrap inside a row), consecutive B chunks
+            if (KS > 0) {
+#pragma unroll
+                for (int k = 0; k < KS; k++)
+                    tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo0 + k * b_inc), idesc8,
+                                 (corr || k) ? 1u : 0u);
+            } else {
+                for (uint32_t k = 0; k < ksteps; k++)
+                    tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo0 + k * b_inc), idesc8,
+                                 (corr || k) ? 1u : 0u);
+            }
+            if (tron) tacc[3] += clock64() - ti_;
+            TC_PROG(1 + mw, (4u << 24) | o);
+            TT(4, tc_commit(t_full + buf));   // accumulator ready for the epilogue
+            TC_PROG(1 + mw, (5u << 24) | o);
+            // bookkeeping for the next own row (off the critical path: the tensor pipe is busy with this row)
+            buf += step, d0 += step * nbs;
+            if (buf >= nbuf) buf -= nbuf, d0 -= nbuf * nbs, bpar ^= 1, first_round = false;
+            o_slot16 += step * (2048u >> 4);
+            if (o_slot16 >= a2_end16) o_slot16 -= a2_wrap16;
+            a_first += step * pitch16;
+            if (a_first >= a_end) a_first -= a_wrap;
+            // hand back every group that lies entirely below what the next own output reads (at the end of an
+            // item that is the next item's first own row, whichever it is: use its first row)
+            const uint32_t g_next = j + step < n_out_rows ? g_first + step : g_item + n_out_rows + n_hp - 1;
+            const uint32_t o_next = j + step < n_out_rows ? o + step : o_item + n_out_rows;
+            while (rel_rows <= g_next) {
+                TT(4, tc_commit(a_empty + rel_g));
+                rel_rows += TC_G;
+                if (++rel_g == ring_g) rel_g = 0;
+            }
+            while (rel2_rows <= o_next) {
+                TT(4, tc_commit(a2_empty + rel2_g));
+                rel2_rows += TC_G;
+                if (++rel2_g == TC_A2_GROUPS) rel2_g = 0;
+            }
+        }
+        // next item: its first row follows this item's last page row
+        o_item += n_out_rows;
+        g_item += n_out_rows + n_hp - 1;
+        a_item += ((n_out_rows + n_hp - 1) % ring_n) * pitch16;
+        if (a_item >= a_end) a_item -= a_wrap;
+    }
+    TC_PROG(1 + mw, 9u << 24);
+    // groups this thread never passed explicitly (the other thread owned the last rows): nothing waits for them
+    if (mw == 0) TT_END(0);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     // ---- shared memory carve-up (all blocks multiples of 128 B)
     uint8_t *btile = smem;
     uint8_t *ring = btile + ((p.btile_bytes + 127) & ~127u);
-    uint8_t *raw = ring + (size_t)(p.ring + 1) * p.row_pitch;  // +1: mirror of slot 0 for (ring-1, 0) pairs
+    uint8_t *raw = ring + (size_t)(p.ring + p.n_hp) * p.row_pitch;  // + mirror slots: slot ring+i repeats slot i (i < n_hp-1)
     uint8_t *a2ring = raw + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127);  // [TC_A2_GROUPS*4][128][16 B] fp16 x 8
-    uint8_t *zeroA = a2ring + TC_A2_GROUPS * TC_G * 2048;                 // 128 x 16 B of zeros (K chunk 1 of A2)
-    uint8_t *b2tile = zeroA + 2048;                                        // [2][nb][16 B]: chunk 0 constants, chunk 1 zeros
+    uint8_t *b2tile = a2ring + TC_A2_GROUPS * TC_G * 2048;                // [2][nb][16 B]: chunk 0 constants, chunk 1 zeros
     uint64_t *bars = (uint64_t *)(b2tile + (size_t)2 * p.nb * 16);
     uint64_t *bar_btile = bars;                       // 1
     uint64_t *raw_full = bars + 1;                    // TC_RAW_GROUPS
@@ -282,6 +518,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint64_t *t_full = a2_empty + TC_A2_GROUPS;       // TC_MAX_BUF
     uint64_t *t_empty = t_full + TC_MAX_BUF;          // TC_MAX_BUF
     uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
+    volatile uint32_t *prog = (volatile uint32_t *)(tmem_ptr + 2);   // [32] per-warp progress (debugging aid, see mbar_wait)
+    if (threadIdx.x < 32) prog[threadIdx.x] = 0;
+    volatile uint32_t *const prog_ = prog;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -293,28 +532,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
             mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, 2);     // one tcgen05.commit per MMA-issuing warp
+            mbar_init(a_empty + i, p.issuers);     // one tcgen05.commit per MMA-issuing thread
         }
         for (int i = 0; i < TC_A2_GROUPS; i++) {
             mbar_init(a2_full + i, 4);     // one arrival per A2 warp
-            mbar_init(a2_empty + i, 2);
+            mbar_init(a2_empty + i, p.issuers);
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, 4 * TC_EPI_GROUPS);
+            mbar_init(t_empty + i, TC_LISTS_PER_CTA / 2);  // one arrival per warp of the epilogue team that owns the row
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero blocks and the B2 tile: B2[t] = -{b1, b2, b1, a1, a2, a1, BIG, pad} as fp16 hi/lo splits of
-    // b = s_n/n and a = thr*norm_n; +inf norm marks padding / constant templates (pad = BIG)
-    for (int i = threadIdx.x; i < 2048 / 16; i += TC_THREADS) ((uint4 *)zeroA)[i] = make_uint4(0, 0, 0, 0);
+    // zero blocks and the B2 tile: B2[t] = {-b1, -b2, -b1, -a1, -a2, -a1, -BIG, 510 | -BIG} as fp16 hi/lo splits of
+    // b = s_n/n and a = thr*norm_n; +inf norm marks padding / constant templates (last entry -BIG: never a candidate)
     for (int t = threadIdx.x; t < p.nb; t += TC_THREADS) {
         const float2 c = p.colconst[t];
         const bool pad = !(c.x < __int_as_float(0x7f800000));
         const float a = pad ? 0.f : p.thr * c.x, b = pad ? 0.f : c.y;
         const __half a1 = __float2half_rn(a), b1 = __float2half_rn(b);
         const __half a2 = __float2half_rn(a - __half2float(a1)), b2 = __float2half_rn(b - __half2float(b1));
-        const __half big = __float2half_rn(-TC_BIG), padh = __float2half_rn(pad ? -TC_BIG : 0.f);
+        const __half big = __float2half_rn(-TC_BIG), padh = __float2half_rn(pad ? -TC_BIG : 510.f);
         __align__(16) __half h[8] = {__hneg(b1), __hneg(b2), __hneg(b1), __hneg(a1), __hneg(a2), __hneg(a1), big, padh};
         *(uint4 *)(b2tile + (size_t)t * 16) = *(const uint4 *)h;
         *(uint4 *)(b2tile + ((size_t)p.nb + t) * 16) = make_uint4(0, 0, 0, 0);
@@ -329,18 +567,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    // every accumulator column starts out holding the bias (epilogue warps own their lane quarter)
-    if (warp >= 12) {
-        const int q = warp & 3, grp = (warp - 12) >> 2;
-        for (int c = grp * 32; c < 512; c += 32 * TC_EPI_GROUPS)
-            tc_st32_const(tmem_base + ((uint32_t)(q * 32) << 16) + c, TC_BIAS);
-        tc_wait_st();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    // the CTA owns all 512 TMEM columns of its SM: the allocation starts at lane 0, column 0.  Using the literal
+    // keeps every TMEM address warp-uniform for the compiler.
+    if (*tmem_ptr != 0) __trap();
+    constexpr uint32_t tmem_base = 0;
 
     // rows this CTA streams through the pipeline (all its items)
     uint32_t total_rows = 0, total_out = 0;
@@ -352,6 +582,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
     }
 
+    // Register re-partition (setmaxnreg, warpgroup granular, first statement of a role): the Toeplitz and A2
+    // warps give registers away, the epilogue warps, which hold two 32-column units at a time, take them.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_ISSUE));
     if (warp == 0) {
         // ================================================================== TMA producer (warp-uniform, one elected lane issues)
         if (elect_one()) {
@@ -362,12 +596,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         uint32_t rg = 0, rgpar = 1;  // raw group and the parity of its PREVIOUS use
         uint32_t in_group = 0, slot = 0;
         bool first_round = true;
+        TT_BEGIN();
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const uint8_t *src = p.inv + (size_t)it.page * p.inv_page_stride + it.x0 + (size_t)it.ys0 * p.pitch;
             const int n_rows = (it.ys1 - it.ys0) + p.n_hp - 1;
             for (int r = 0; r < n_rows; r++, src += p.pitch) {
-                if (in_group == 0 && !first_round) mbar_wait(raw_empty + rg, rgpar);
+                if (in_group == 0 && !first_round) TT(0, mbar_wait(raw_empty + rg, rgpar, p.wd, 1, slot, prog));
                 if (elect_one()) {
                     mbar_expect_tx(raw_full + rg, row_bytes);
                     tma_bulk_g2s(raw + slot * TC_RAW_BYTES, src, row_bytes, raw_full + rg);
@@ -382,119 +617,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             }
         }
         if (in_group != 0 && elect_one()) mbar_arrive(raw_full + rg);  // the last, partial group
+        if (lane == 0) TT_END(32);
     } else if (warp == 1 || warp == 2) {
-        // ================================================================== MMA issuers (two warps)
-        // One warp cannot issue fast enough (its serial stream of descriptor arithmetic, R2UR, UTCIMMA and
-        // commits costs more per output row than the tensor core needs), so output rows alternate between
-        // two issuing warps; they touch different accumulators, so their relative order is free.  A ring
-        // group goes back to its producer when BOTH issuers have moved past it: each commits to the
-        // group's "empty" barrier (count 2) once its next output no longer reads the group --
-        // tcgen05.commit only tracks the MMAs of the committing thread.
-        const uint32_t mw = warp - 1;
-        const uint32_t idesc8 = (2u << 4)                          // D format: S32
-                                | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
-                                | (0u << 15) | (0u << 16)          // A, B: K-major
-                                | ((uint32_t)(p.nb >> 3) << 17)    // N
-                                | ((128u >> 4) << 24);             // M = 128
-        const uint32_t idesc16 = (1u << 4)                         // D format: F32 (same TMEM columns, read as fp32)
-                                 | (0u << 7) | (0u << 10)          // A, B: F16
-                                 | ((uint32_t)(p.nb >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp;
-        const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4;
-        const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
-        const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
-        const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
-        const uint32_t desc_hi = (128u >> 4) | (1u << 14);       // SBO = 128 B, version = 1
-        const uint32_t a_lo0 = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
-        const uint32_t b_lo0 = ((smem_u32(btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
-        const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
-        const uint32_t a2_addr16 = (smem_u32(a2ring) & 0x3FFFFu) >> 4, zero16 = (smem_u32(zeroA) & 0x3FFFFu) >> 4;
-        const uint32_t b2_lo = ((smem_u32(b2tile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
-        const bool corr = p.dbg_acc == nullptr;
-        mbar_wait(bar_btile, 0);
-        uint32_t g_first = 0;                    // global page-row index of the current output row's first row
-        uint32_t s_first = 0;                    // its ring slot (g_first mod ring_n)
-        uint32_t rel_g = 0, rel_rows = TC_G;     // page-row groups: next to hand back / rows covered once it is
-        uint32_t new_g = 0, new_par = 0, rows_ready = 0;
-        uint32_t o = 0;                          // global output-row index (A2 ring)
-        uint32_t o_slot = 0;                     // o mod (TC_A2_GROUPS * TC_G)
-        uint32_t rel2_g = 0, rel2_rows = TC_G, new2_g = 0, new2_par = 0, rows2_ready = 0;
-        uint32_t buf = 0, bpar = 0;              // accumulator sequence (both warps count all jobs)
-        bool first_round = true;
-        Item it;
-        for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
-            const int n_out_rows = it.ys1 - it.ys0;
-            for (int j = 0; j < n_out_rows; j++, o++) {
-                if ((o & 1u) == mw) {
-                    // hand back every group that lies entirely below what this output reads
-                    while (rel_rows <= g_first) {
-                        if (elect_one()) tc_commit(a_empty + rel_g);
-                        __syncwarp();
-                        rel_rows += TC_G;
-                        if (++rel_g == ring_g) rel_g = 0;
-                    }
-                    while (rel2_rows <= o) {
-                        if (elect_one()) tc_commit(a2_empty + rel2_g);
-                        __syncwarp();
-                        rel2_rows += TC_G;
-                        if (++rel2_g == TC_A2_GROUPS) rel2_g = 0;
-                    }
-                    while (rows_ready < g_first + n_hp) {   // page rows this output needs
-                        mbar_wait(a_full + new_g, new_par);
-                        rows_ready += TC_G;
-                        if (++new_g == ring_g) new_g = 0, new_par ^= 1;
-                    }
-                    while (corr && rows2_ready < o + 1) {   // its A2 row
-                        mbar_wait(a2_full + new2_g, new2_par);
-                        rows2_ready += TC_G;
-                        if (++new2_g == TC_A2_GROUPS) new2_g = 0, new2_par ^= 1;
-                    }
-                    if (!first_round) mbar_wait(t_empty + buf, bpar ^ 1);
-                    tc_fence_after();
-                    {
-                        const bool leader = elect_one();
-                        const uint32_t d0 = tmem_base + buf * p.nbs;
-                        uint32_t al0 = a_lo0 + s_first * pitch16, bl0 = b_lo0;
-                        for (uint32_t k = 0; k < ksteps; k++) {
-                            if (leader) tc_mma_i8(d0, ((uint64_t)desc_hi << 32) | al0, ((uint64_t)desc_hi << 32) | bl0, idesc8);
-                            al0 += a_inc;
-                            if (al0 >= a_end) al0 -= a_wrap;
-                            bl0 += 2 * b_lbo16;
-                        }
-                        if (leader) {
-                            if (corr) {
-                                // d += A2 . B2^T  in fp32: K chunk 0 = this output row's statistics, chunk 1 = zeros
-                                const uint32_t slot16 = a2_addr16 + o_slot * (2048u >> 4);
-                                const uint32_t lo = slot16 | ((zero16 - slot16) << 16);
-                                tc_mma_f16(d0, ((uint64_t)desc_hi << 32) | lo, ((uint64_t)desc_hi << 32) | b2_lo, idesc16);
-                            }
-                            tc_commit(t_full + buf);   // accumulator ready for the epilogue
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (++buf == nbuf) buf = 0, bpar ^= 1, first_round = false;
-                if (++o_slot == TC_A2_GROUPS * TC_G) o_slot = 0;
-                g_first++;
-                if (++s_first == ring_n) s_first = 0;
+        // ================================================================== MMA issuers (tc_mma_role)
+        if ((int)warp <= p.issuers && elect_one()) {
+            TcSmem sm = {btile, ring, a2ring, b2tile, bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty, prog};
+            const uint32_t mw = warp - 1;
+            switch (p.ksteps) {
+                case 6: tc_mma_role<6>(p, sm, mw); break;
+                case 7: tc_mma_role<7>(p, sm, mw); break;
+                case 8: tc_mma_role<8>(p, sm, mw); break;
+                default: tc_mma_role<0>(p, sm, mw); break;
             }
-            // the item's last n_hp-1 page rows are not the first row of any output
-            g_first += n_hp - 1;
-            s_first += n_hp - 1;
-            while (s_first >= ring_n) s_first -= ring_n;
         }
-    } else if (warp >= 4 && warp < 8) {
+        __syncwarp();
+    }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_TOEPLITZ));
         // ================================================================== Toeplitz expansion
         // one warp per page row, four rows (one group) in flight per handshake
         const int w = warp - 4;
-        const bool mirror = p.np == 16;
+        const uint32_t n_mirror = p.n_hp - 1;   // slots 0 .. n_hp-2 are stored twice, so an output row never wraps
         const uint32_t ring_g = p.ring_groups;
         uint32_t rg = 0, rgpar = 0, ag = 0, agpar = 1;
         bool first_round = true;
+        TT_BEGIN();
         for (uint32_t g0 = 0; g0 < total_rows; g0 += TC_G) {
-            mbar_wait(raw_full + rg, rgpar);
-            if (!first_round) mbar_wait(a_empty + ag, agpar);
-            if (g0 + w < total_rows) {
+            if (lane == 0) TC_PROG(warp, g0);
+            TT(0, mbar_wait(raw_full + rg, rgpar, p.wd, 2, g0, prog));
+            if (!first_round) TT(1, mbar_wait(a_empty + ag, agpar, p.wd, 3, g0, prog));
+            if (g0 + w < total_rows && !(TC_EXP && (p.dbg_mode & 16))) {
                 const uint32_t *rw = (const uint32_t *)(raw + (rg * TC_G + w) * TC_RAW_BYTES);
                 const uint32_t s = ag * TC_G + w;
                 uint8_t *dst = ring + (size_t)s * p.row_pitch;
@@ -508,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     o4.z = __funnelshift_r(w2, w3, sh);
                     o4.w = __funnelshift_r(w3, w4, sh);
                     *(uint4 *)(dst + ee * 16) = o4;
-                    if (mirror && s == 0) *(uint4 *)(ring + (size_t)p.ring * p.row_pitch + ee * 16) = o4;
+                    if (s < n_mirror) *(uint4 *)(dst + (size_t)p.ring * p.row_pitch + ee * 16) = o4;
                 }
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
@@ -520,12 +672,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             if (++rg == TC_RAW_GROUPS) rg = 0, rgpar ^= 1;
             if (++ag == ring_g) ag = 0, agpar ^= 1, first_round = false;
         }
-    } else if (warp >= 8 && warp < 12) {
+        if (w == 0 && lane == 0) TT_END(16);
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_A2));
         // ================================================================== A2 rows: window statistics -> fp16 operand
         // One warp per output row, four rows per handshake.  For window m of output row y:
-        //   A2 = {S_hi, S_hi, S_lo, P_1, P_1, P_2, V, BIG}   (S = s_p split at bit 6; P = norm_p split hi/lo)
+        //   A2 = {S_hi, S_hi, S_lo, P_1, P_1, P_2, V, 2^15}   (S = s_p split at bit 6; P = norm_p split hi/lo)
         // V = BIG when the window can never hit: x outside [1, r_w-n_w] (ncc.rs:281) or a constant window
-        // (norm_p = +inf marker: rnorm_p = inf in the reference, ncc.cpp:216-220).
+        // (norm_p = +inf marker: rnorm_p = inf in the reference, ncc.cpp:216-220).  V = -BIG (always a
+        // candidate, S = P = 0) when b_max*S + a_max*P could push F below 2^23, where its bits stop being linear.
         const int w = warp - 8;
         uint32_t ag = 0, agpar = 1;
         bool first_round = true;
@@ -533,8 +688,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         uint32_t item_o0 = 0;  // global output index of the current item's first row
         Item it;
         bool have = get_item(p, cur_idx, it);
+        TT_BEGIN();
         for (uint32_t o0 = 0; o0 < total_out; o0 += TC_G) {
-            if (!first_round) mbar_wait(a2_empty + ag, agpar);
+            if (lane == 0) TC_PROG(warp, o0);
+            if (!first_round) TT(0, mbar_wait(a2_empty + ag, agpar, p.wd, 4, o0, prog));
             const uint32_t o = o0 + w;
             if (o < total_out) {
                 while (have && o >= item_o0 + (uint32_t)(it.ys1 - it.ys0)) {  // advance to the item that owns row o
@@ -550,21 +707,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int m = lane + 32 * i, gx = it.x0 + m;
-                    const bool ok = gx >= 1 && gx <= p.r_w - p.n_w;
+                    const bool ok = gx >= 1 && gx <= p.r_w - p.n_w && !(TC_EXP && (p.dbg_mode & 8));
                     sv[i] = ok ? __ldg(p.sp + rowoff + m) : 0u;
                     pv[i] = ok ? __ldg(p.pf + rowoff + m) : __int_as_float(0x7f800000);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < 4 && !(TC_EXP && (p.dbg_mode & 32)); i++) {
                     const int m = lane + 32 * i;
                     const bool valid = pv[i] < __int_as_float(0x7f800000);
-                    const uint32_t s = valid ? sv[i] : 0u;
-                    const float P = valid ? pv[i] : 0.f;
+                    const bool lin = valid && (p.bmax * (float)sv[i] + p.amax * pv[i] <= TC_KCAP);
+                    const uint32_t s = lin ? sv[i] : 0u;
+                    const float P = lin ? pv[i] : 0.f;
                     const float s_hi = (float)(s & ~63u), s_lo = (float)(s & 63u);
                     const __half p1 = __float2half_rn(P);
                     const __half p2 = __float2half_rn(P - __half2float(p1));
                     const __half shi = __float2half_rn(s_hi), slo = __float2half_rn(s_lo);
-                    const __half v = __float2half_rn(valid ? 0.f : TC_BIG), k = __float2half_rn(TC_BIG);
+                    const __half v = __float2half_rn(valid ? (lin ? 0.f : -TC_BIG) : TC_BIG), k = __float2half_rn(32768.f);
                     __align__(16) __half h[8] = {shi, shi, slo, p1, p1, p2, v, k};
                     *(uint4 *)(dst + m * 16) = *(const uint4 *)h;
                 }
@@ -574,71 +732,105 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             if (lane == 0) mbar_arrive(a2_full + ag);
             if (++ag == TC_A2_GROUPS) ag = 0, agpar ^= 1, first_round = false;
         }
-    } else if (warp >= 12) {
-        // ================================================================== epilogue (8 warps, 2 per TMEM lane quarter)
-        // The accumulator holds fp32 2^23 + d: one 3-input max per column pair, one vote per 32 columns;
-        // after reading, the unit is re-armed with the bias for its next use.
+        if (w == 0 && lane == 0) TT_END(24);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
+        // ================================================================== epilogue (16 warps = 2 teams x 4 lane quarters x 2)
+        // The accumulator holds the bits of fp32 C0 + d: one 3-input max per column pair (a tree, so the
+        // FMNMX3s are independent), one vote per 32 columns.  Output rows alternate between two TEAMS of 8
+        // warps, so a warp pays the per-row overhead (barrier wait, fences, arrive) only every second row;
+        // inside a team the two warps of a lane quarter take the even / odd 32-column units.  Two units are
+        // in registers at a time; the accumulator goes back to the MMA thread as soon as the warp's LAST unit
+        // has landed, before it is screened.
         const int e = warp - 12;
         const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
-        const int grp = e >> 2;
+        const int team = (e >> 2) & 1, sub = e >> 3;
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t nbuf = p.nbuf;
-        const int nunits = p.nunits, urot = p.nunits % TC_EPI_GROUPS;
-        const float T = p.dbg_acc ? 3.0e38f : 8388608.f - TC_MARGIN;  // 2^23 - margin
-        int ufirst = grp;  // first unit of the current buffer that belongs to this warp
-        uint32_t buf = 0, bpar = 0;
-        Hit *my_list = p.cands + (size_t)(blockIdx.x * 8 + e) * p.cand_cap;
+        const int nunits = p.nunits;
+        const float T = p.dbg_acc ? 3.0e38f : TC_C0 - TC_MARGIN;
+        uint32_t buf = team, bpar = 0;            // accumulator of this team's next row (row index mod nbuf) and its phase
+        Hit *my_list = p.cands + (size_t)(blockIdx.x * TC_LISTS_PER_CTA + e) * p.cand_cap;
         uint32_t my_count = 0;
+        uint32_t orow0 = 0;                       // global output-row index of the current item's first row
+        const bool no_ld = TC_EXP && (p.dbg_mode & 1), no_screen = TC_EXP && (p.dbg_mode & 2);
+        TT_BEGIN();
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int gx = it.x0 + m;
-            for (int y = it.ys0; y < it.ys1; y++) {
-                mbar_wait(t_full + buf, bpar);
+            for (int y = it.ys0 + (int)((team - orow0) & 1u); y < it.ys1; y += 2) {
+                if (lane == 0) TC_PROG(warp, (uint32_t)(y - it.ys0) + orow0);
+                TT(0, mbar_wait(t_full + buf, bpar, p.wd, 20 + team, y, prog));
                 tc_fence_after();
                 const uint32_t tb = tlane + buf * p.nbs;
-                if (p.dbg_mode != 1) {
-                    for (int u = ufirst; u < nunits; u += TC_EPI_GROUPS) {
-                        uint32_t v[32];
-                        tc_ld32(tb + u * 32, v);
-                        tc_wait_ld32(v);
-                        if (p.dbg_mode == 5 || p.dbg_mode == 6) {  // timing experiments: TMEM traffic only
-                            if (v[3] == 0x7fffffffu && v[29] == 0x12345u) my_count++;
-                            if (p.dbg_mode == 6) tc_st32_const(tb + u * 32, TC_BIAS);
-                            continue;
-                        }
-                        float mx = __uint_as_float(v[0]);
+                auto release = [&]() {  // every tcgen05.ld of this row has completed: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + buf);
+                };
+                auto screen = [&](uint32_t (&v)[32], int u) {
+                    float t[11];
 #pragma unroll
-                        for (int j = 1; j < 31; j += 2)
-                            asm("max.f32 %0, %1, %2, %3;"
-                                : "=f"(mx)
-                                : "f"(mx), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
-                        mx = fmaxf(mx, __uint_as_float(v[31]));
-                        if (p.dbg_acc && p.dbg_col >= u * 32 && p.dbg_col < u * 32 + 32) {
-                            const uint32_t a = tc_ld1(tb + p.dbg_col);
-                            tc_wait_ld();
-                            if (gx >= 1 && gx <= p.r_w - p.n_w) p.dbg_acc[(size_t)y * p.r_w + gx] = a - TC_BIAS;
-                        }
-                        if (__any_sync(0xffffffffu, mx >= T)) {
-                            // rare: some lane of the warp has a survivor among these 32 columns
-                            uint32_t mask = 0;
+                    for (int j = 0; j < 10; j++)
+                        asm("max.f32 %0, %1, %2, %3;"
+                            : "=f"(t[j])
+                            : "f"(__uint_as_float(v[3 * j])), "f"(__uint_as_float(v[3 * j + 1])), "f"(__uint_as_float(v[3 * j + 2])));
+                    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                    float a, b, c, mx;
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(t[0]), "f"(t[1]), "f"(t[2]));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(t[3]), "f"(t[4]), "f"(t[5]));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(c) : "f"(t[6]), "f"(t[7]), "f"(t[8]));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(t[9]), "f"(t[10]), "f"(a));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(b), "f"(c));
+                    if (__any_sync(0xffffffffu, mx >= T)) {
+                        // rare: some lane of the warp has a survivor among these 32 columns
+                        uint32_t mask = 0;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= T ? 1u : 0u) << j;
-                            append_candidates(my_list, p.cand_cap, my_count, mask, p.col_base + u * 32, it.page, gx, y);
-                        }
-                        tc_st32_const(tb + u * 32, TC_BIAS);  // re-arm the unit for the next output row
+                        for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= T ? 1u : 0u) << j;
+                        append_candidates(my_list, p.cand_cap, my_count, mask, p.col_base + u * 32, it.page, gx, y);
                     }
-                    tc_wait_st();
+                };
+                if (p.dbg_acc && sub == 0) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
+                    const uint32_t a = tc_ld1(tb + p.dbg_col);
+                    tc_wait_ld();
+                    if (gx >= 1 && gx <= p.r_w - p.n_w) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + buf);
-                if (++buf == nbuf) buf = 0, bpar ^= 1;
-                ufirst -= urot;
-                if (ufirst < 0) ufirst += TC_EPI_GROUPS;
+                // this warp's units: sub, sub + 2, sub + 4, sub + 6 (nunits <= 8), two at a time
+                const int u0 = sub, u1 = sub + 2, u2 = sub + 4, u3 = sub + 6;
+                const bool h0 = u0 < nunits && !no_ld, h1 = u1 < nunits && !no_ld, h2 = u2 < nunits && !no_ld,
+                           h3 = u3 < nunits && !no_ld;
+                uint32_t va[32], vb[32];
+                if (h0) tc_ld32(tb + u0 * 32, va);
+                if (h1) tc_ld32(tb + u1 * 32, vb);
+                if (h0) tc_wait_ld32(va);
+                if (h1) tc_wait_ld32(vb);
+                if (!h2) {
+                    release();
+                    if (!no_screen) {
+                        if (h0) screen(va, u0);
+                        if (h1) screen(vb, u1);
+                    }
+                } else {
+                    if (!no_screen) screen(va, u0);
+                    tc_ld32(tb + u2 * 32, va);
+                    if (!no_screen) screen(vb, u1);
+                    if (h3) tc_ld32(tb + u3 * 32, vb);
+                    tc_wait_ld32(va);
+                    if (h3) tc_wait_ld32(vb);
+                    release();
+                    if (!no_screen) {
+                        screen(va, u2);
+                        if (h3) screen(vb, u3);
+                    }
+                }
+                buf += 2;
+                if (buf >= nbuf) buf -= nbuf, bpar ^= 1;
             }
+            orow0 += it.ys1 - it.ys0;
         }
-        if (lane == 0) p.cand_count[blockIdx.x * 8 + e] = my_count;
+        if (lane == 0) p.cand_count[blockIdx.x * TC_LISTS_PER_CTA + e] = my_count;
+        if (e == 0 && lane == 0) TT_END(8);
     }
 
     // ---- teardown
@@ -727,11 +919,11 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int row_pitch, int nb)
+static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_hp, int row_pitch, int nb)
 {
-    return ((btile_bytes + 127) & ~127u) + (size_t)(ring + 1) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
-           (size_t)TC_A2_GROUPS * TC_G * 2048 + 2048 + (size_t)2 * nb * 16 +
-           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 2 * TC_MAX_BUF) * 8 + 64;
+    return ((btile_bytes + 127) & ~127u) + (size_t)(ring + n_hp) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
+           (size_t)TC_A2_GROUPS * TC_G * 2048 + (size_t)2 * nb * 16 +
+           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 2 * TC_MAX_BUF) * 8 + 64 + 128;
 }
 
 int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
@@ -753,7 +945,7 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     if (n_w * n_h > 256) return 0;
     // largest NB (multiple of 16, <= 256) whose B tile fits next to the rings
     int nb_max = 256;
-    while (nb_max >= 32 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, row_pitch, nb_max) > TC_SMEM_BUDGET) nb_max -= 32;
+    while (nb_max >= 32 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)n_hp, row_pitch, nb_max) > TC_SMEM_BUDGET) nb_max -= 32;
     if (nb_max < 32) return 0;
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
     // a multiple of 32: the epilogue works in 32-column units and every column of a unit must be written by the
@@ -765,6 +957,8 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
     const float inf = INFINITY;
     for (auto &c : cst) c = make_float2(inf, 0.f);
+    tc.blk_bmax.assign(tc.n_blocks, 0.f);
+    tc.blk_normmax.assign(tc.n_blocks, 0.f);
     for (uint32_t i = 0; i < n_tpl; i++) {
         const uint32_t blk = i / tc.nb, n = i % tc.nb;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
@@ -777,6 +971,10 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
         const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
         cst[(size_t)blk * tc.nb + n] = make_float2(ok ? (float)norm_n : inf, (float)(ti.s_n * ti.n_recip));
         tof[(size_t)blk * tc.nb + n] = bank_index[i];
+        if (ok) {
+            tc.blk_bmax[blk] = std::max(tc.blk_bmax[blk], (float)(ti.s_n * ti.n_recip));
+            tc.blk_normmax[blk] = std::max(tc.blk_normmax[blk], (float)norm_n);
+        }
     }
     if (cudaMalloc(&tc.b_tiles, bt.size()) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.consts, cst.size() * sizeof(float2)) != cudaSuccess) return -1;
@@ -803,7 +1001,7 @@ bool tc_class_supported(const TcClass &tc) { return tc.supported; }
 void tc_workspace_release(TcWorkspace &) {}
 
 cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
-                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc, int dbg_pos)
+                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc, int dbg_pos, TcHook *hook)
 {
     if (!tc.supported) return cudaErrorNotSupported;
     TcParams p;
@@ -821,13 +1019,18 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.nb = tc.nb;
     p.nunits = (tc.nb + 31) / 32;
     p.nbs = (tc.nb + 31) & ~31;
-    p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
+    // An EVEN number of accumulators: with two issuing threads / two epilogue teams on alternate rows, accumulator b is then
+    // always written by thread b%2 and read by team b%2, so each of them sees every phase of its barriers.  (With an odd
+    // count the owners alternate, a waiter can fall two phases behind and the parity test aliases.)
+    p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF) & ~1;
     p.ring_groups = (p.n_hp + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;  // rows y..y+n_hp-1 may straddle one more group
     p.ring = p.ring_groups * TC_G;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
     p.n_entries = tc.np == 16 ? 128 : 144;
     p.btile_bytes = 2 * tc.ksteps * tc.nb * 16;
-    p.thr = (float)a.thr_d;
+    // the screen only has to pass a SUPERSET of the hits: |sim| <= 1 up to rounding, so thresholds beyond +-2 are
+    // clamped (keeps thr*norm_n inside the fp16 range); cand_exact_kernel applies the real threshold
+    p.thr = (float)std::min(std::max(a.thr_d, -2.0), 2.0);
     p.sp = a.sp;
     p.pf = a.pf;
     p.spitch = a.spitch;
@@ -835,12 +1038,13 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.cands = a.cands;
     p.cand_cap = a.cand_cap;
     p.cand_count = a.cand_count;
+    p.wd = a.cand_max ? a.cand_max + 1 : nullptr;   // api.cu: flags[4..9] follow the candidate high-water mark
     p.n_pages = n_pages;
     const int xs = a.r_w - (int)tc.n_w + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
     if (xs <= 0 || ys <= 0) return cudaSuccess;
     p.n_xstrips = (xs + 127) / 128;
     p.n_ysegs = (ys + TC_YSEG - 1) / TC_YSEG;
-    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.row_pitch, p.nb);
+    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_hp, p.row_pitch, p.nb);
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int items = n_pages * p.n_xstrips * p.n_ysegs;
@@ -850,22 +1054,75 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     {
         const char *dm = getenv("FOCR_TC_DBG");
         p.dbg_mode = dm ? atoi(dm) : 0;
+        const char *is = getenv("FOCR_TC_ISSUERS");  // honoured in every build: 1 = a single issuing thread
+        p.issuers = is && atoi(is) == 1 ? 1 : 2;
+        const char *sp = getenv("FOCR_TC_SPIN");
+        p.spin = sp ? atoi(sp) : 3;
     }
-    for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
+    uint4 *wdlog = nullptr;
+    if (getenv("FOCR_TC_WDLOG") && cudaMalloc((void **)&wdlog, (size_t)grid * 32 * sizeof(uint4)) == cudaSuccess) {
+        cudaMemsetAsync(wdlog, 0, (size_t)grid * 32 * sizeof(uint4), st);
+        cudaMemcpyToSymbolAsync(g_wdlog, &wdlog, sizeof(wdlog), 0, cudaMemcpyHostToDevice, st);
+    }
+    const char *trace_path = dbg_acc ? nullptr : getenv("FOCR_TC_TRACE");
+        for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
+        if (trace_path && cudaMalloc((void **)&p.trace, (size_t)64 * 8) == cudaSuccess)
+            cudaMemsetAsync(p.trace, 0, (size_t)64 * 8, st);
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
         p.colconst = tc.consts + (size_t)blk * tc.nb;
         p.col_base = blk * tc.nb;
+        p.bmax = tc.blk_bmax[blk] * 1.001f;
+        p.amax = std::max(p.thr * tc.blk_normmax[blk], 0.f) * 1.001f;
         scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
+        if (wdlog) {
+            std::vector<uint4> h((size_t)grid * 32);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h.data(), wdlog, h.size() * sizeof(uint4), cudaMemcpyDeviceToHost);
+            unsigned int wdh[10] = {0};
+            if (p.wd) cudaMemcpy(wdh, p.wd, sizeof(wdh), cudaMemcpyDeviceToHost);
+            if (wdh[0]) {
+                const unsigned cta = wdh[3];
+                fprintf(stderr, "[focr] scan_tc stalled: box %ux%u nb %d nbuf %d ring %d; first report tag %u info %u CTA %u warp %u\n", tc.n_w,
+                        tc.n_h, p.nb, p.nbuf, p.ring, wdh[1], wdh[2], cta, wdh[4]);
+                uint32_t pg[32];
+                cudaMemcpyFromSymbol(pg, g_wdprog, sizeof(pg));
+                fprintf(stderr, "   progress snapshot of CTA %u (taken by warp %u, tag %u): T0 stage %u o %u | T1 stage %u o %u | toeplitz g0", wdh[7], wdh[8],
+                        wdh[9], pg[1] >> 24, pg[1] & 0xFFFFFF, pg[2] >> 24, pg[2] & 0xFFFFFF);
+                for (int w = 4; w < 8; w++) fprintf(stderr, " %u", pg[w]);
+                fprintf(stderr, " | a2 o0");
+                for (int w = 8; w < 12; w++) fprintf(stderr, " %u", pg[w]);
+                fprintf(stderr, " | epilogue rows");
+                for (int w = 12; w < 28; w++) fprintf(stderr, " %u", pg[w]);
+                fprintf(stderr, "\n");
+                for (int w = 0; w < 28 && getenv("FOCR_TC_WDLOG")[0] == '2'; w++) {
+                    const uint4 v = h[(size_t)cta * 32 + w];
+                    fprintf(stderr, "   warp %2d: tag %2u info %6u parity %u bar@%u\n", w, v.x, v.y, v.z, v.w);
+                }
+            }
+            cudaMemsetAsync(wdlog, 0, (size_t)grid * 32 * sizeof(uint4), st);
+        }
+        if (p.trace) {  // dump CTA 0's per-row timestamps: one file per (box size, N-block) launch, last launch wins
+            std::vector<long long> h(64);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h.data(), p.trace, h.size() * 8, cudaMemcpyDeviceToHost);
+            cudaFree(p.trace);
+            p.trace = nullptr;
+            const std::string fn = std::string(trace_path) + "." + std::to_string(tc.n_w) + "x" + std::to_string(tc.n_h) + "." + std::to_string(blk);
+            if (FILE *f = fopen(fn.c_str(), "wb")) {
+                fwrite(h.data(), 8, h.size(), f);
+                fclose(f);
+            }
+        }
         if (dbg_acc) continue;
         // the per-warp candidate lists are rewritten by every launch: run the exact pass right away
         CandArgs ca;
         ca.cands = a.cands;
         ca.cand_cap = a.cand_cap;
-        ca.n_lists = (uint32_t)grid * 8;
+        ca.n_lists = (uint32_t)grid * TC_LISTS_PER_CTA;
         ca.cand_count = a.cand_count;
         ca.cand_max = a.cand_max;
         ca.tpl_of = tc.tpl_of;
@@ -884,8 +1141,10 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
         ca.n_d = (double)(tc.n_w * tc.n_h);
         ca.thr_d = a.thr_d;
         ca.sink = a.sink;
-        cand_exact_kernel<<<grid * 8, 256, 0, st>>>(ca);
+        if (hook) hook->exact_begin();
+        cand_exact_kernel<<<grid * TC_LISTS_PER_CTA, 256, 0, st>>>(ca);
         e = cudaGetLastError();
+        if (hook) hook->exact_end();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
     }

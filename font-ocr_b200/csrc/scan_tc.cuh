@@ -1,9 +1,13 @@
 // scan_tc.cuh -- host interface of the tcgen05 correlation kernel (scan_tc.cu).
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace focr {
+
+constexpr int TC_LISTS_PER_CTA = 16;  // epilogue warps per CTA, each with a private candidate list
 
 // per box size: the template bank re-laid out as the B operand of tcgen05.mma (K-major, no swizzle)
 struct TcClass {
@@ -17,10 +21,18 @@ struct TcClass {
     uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]
     float2 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
     uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
+    std::vector<float> blk_bmax, blk_normmax;  // host, per N-block: max s_n/n and max norm_n over its real columns
 };
 
 struct TcWorkspace {
     void *work_counter = nullptr;  // device: dynamic tile scheduler counter
+};
+
+// optional instrumentation around the exact pass (api.cu times it as its own stage)
+struct TcHook {
+    virtual void exact_begin() {}
+    virtual void exact_end() {}
+    virtual ~TcHook() {}
 };
 
 int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
@@ -30,6 +42,7 @@ bool tc_class_supported(const TcClass &tc);
 void tc_workspace_release(TcWorkspace &ws);
 // dbg_acc/dbg_pos: parity probe -- store the raw numerators of the class's dbg_pos-th template
 cudaError_t launch_scan_tc(TcWorkspace &ws, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
-                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc = nullptr, int dbg_pos = -1);
+                           cudaStream_t st, int *n_launches, uint32_t *dbg_acc = nullptr, int dbg_pos = -1,
+                           TcHook *hook = nullptr);
 
 }  // namespace focr

@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps
                         : "memory");
                 }
             }
+            const long long ti = clock64();
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ub_smem_u32(&bar)) : "memory");
+            cycles[gridDim.x + blockIdx.x] = ti - t0;  // when the issuing thread got past the last tcgen05.mma
         }
         __syncwarp();
         uint32_t done;
@@ -84,7 +86,131 @@ __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps
     }
 }
 
+// TMEM <-> register traffic micro-benchmark: `nw` warps (multiple of 4) each run `iters` rounds of
+// tcgen05.ld 32x32b.x32 (+ wait) and/or tcgen05.st 32x32b.x32 over rotating 32-column units of their lane
+// quarter, optionally while one more warp keeps the tensor core busy with `mma_count` x 7 MMAs of N = mma_n.
+// out[2*blk] = slowest ld/st warp's cycles, out[2*blk+1] = the MMA warp's cycles.
+__global__ void __launch_bounds__(32 * 17, 1) tmem_bench_kernel(int nw, int mode, int iters, int mma_n, int mma_count, long long *out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    __shared__ long long wc[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ksteps = 7, n = mma_n > 0 ? mma_n : 16;
+    for (int i = threadIdx.x; i < (ksteps * 2 * (128 + n) * 16) / 4; i += blockDim.x) ((uint32_t *)smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ub_smem_u32(&bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ub_smem_u32(&tmem_ptr)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_ptr;
+    if (warp < nw) {
+        const int q = warp & 3, grp = warp >> 2, ngrp = nw >> 2;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t sink = 0;
+        int u = grp;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; it++) {
+            const uint32_t ta = tl + (uint32_t)u * 32;
+            if (mode != 2) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(ta));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (mode == 3) {
+                    float mx = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int j = 1; j < 31; j += 2)
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])));
+                    mx = fmaxf(mx, __uint_as_float(v[31]));
+                    if (__any_sync(0xffffffffu, mx >= 3.0e38f)) sink++;
+                } else {
+                    sink += v[3] ^ v[29];
+                }
+            }
+            if (mode == 1 || mode == 2) {
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                    "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(ta),
+                    "r"(0x4B000000u)
+                    : "memory");
+            }
+            u += ngrp;
+            if (u >= 16) u -= 16;
+        }
+        if (mode == 1 || mode == 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        const long long t1 = clock64();
+        if (lane == 0) wc[warp] = (t1 - t0) + (sink == 0x12345678u ? 1 : 0);
+    } else if (warp == nw && mma_n > 0) {
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+        const uint32_t a0 = ((ub_smem_u32(smem) & 0x3FFFFu) >> 4) | ((2048u >> 4) << 16);
+        const uint32_t bbase = ub_smem_u32(smem) + ksteps * 2 * 2048;
+        const uint32_t b0 = ((bbase & 0x3FFFFu) >> 4) | (((uint32_t)n * 16u >> 4) << 16);
+        const int nbs = (n + 31) & ~31, nacc = 512 / nbs;
+        uint32_t elected;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        __syncwarp();
+        const long long t0 = clock64();
+        if (elected) {
+            for (int it = 0; it < mma_count; it++) {
+                const uint32_t d = tmem_base + (uint32_t)((it % nacc) * nbs);
+                for (int k = 0; k < ksteps; k++) {
+                    const uint64_t ad = ((uint64_t)desc_hi << 32) | (a0 + (uint32_t)k * 2 * (2048 >> 4));
+                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (b0 + (uint32_t)k * 2 * ((uint32_t)n * 16u >> 4));
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                        "l"(ad), "l"(bd), "r"(idesc), "r"(1)
+                        : "memory");
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ub_smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
+        uint32_t done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(ub_smem_u32(&bar)), "r"(0) : "memory");
+        } while (!done);
+        const long long t1 = clock64();
+        if (lane == 0) out[2 * blockIdx.x + 1] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long m = 0;
+        for (int i = 0; i < nw; i++) m = wc[i] > m ? wc[i] : m;
+        out[2 * blockIdx.x] = m;
+        if (mma_n <= 0) out[2 * blockIdx.x + 1] = 0;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 }  // namespace focr
+
+static double g_last_issue_cycles = 0;
+// cycles (median over SMs) the issuing thread of the last focr_bench_umma_i8 run needed to get past its last
+// tcgen05.mma: with the total this shows how far ahead of the tensor pipe an issuing thread may run
+extern "C" double focr_bench_umma_issue_cycles(void) { return g_last_issue_cycles; }
 
 // n: MMA N (multiple of 16, <= 256); returns the median over SMs of cycles per tcgen05.mma and the wall time
 extern "C" int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
@@ -99,7 +225,7 @@ extern "C" int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, i
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
     long long *d = nullptr;
-    if (cudaMalloc((void **)&d, sms * 8) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
+    if (cudaMalloc((void **)&d, sms * 16) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
     const size_t smem = (size_t)ksteps * 2 * (128 + n) * 16 + 1024;
     if (cudaFuncSetAttribute(umma_i8_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaFuncSetAttribute");
     cudaEvent_t e0, e1;
@@ -113,13 +239,49 @@ extern "C" int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, i
     if (e != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, std::string("umma bench: ") + cudaGetErrorString(e));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    std::vector<long long> h(sms);
-    cudaMemcpy(h.data(), d, sms * 8, cudaMemcpyDeviceToHost);
+    std::vector<long long> h(sms * 2);
+    cudaMemcpy(h.data(), d, sms * 16, cudaMemcpyDeviceToHost);
     cudaFree(d);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    std::sort(h.begin(), h.end());
+    std::sort(h.begin(), h.begin() + sms);
+    std::sort(h.begin() + sms, h.end());
     *cycles_per_mma = (double)h[sms / 2] / ((double)iters * ksteps);
+    if (iters < 0) *cycles_per_mma = 0;
+    g_last_issue_cycles = (double)h[sms + sms / 2];
     *ms_total = ms;
+    return FOCR_OK;
+}
+
+// TMEM load/store micro-benchmark (see tmem_bench_kernel): cycles per 32x32b.x32 round per warp (median over SMs of the
+// slowest warp) and cycles per MMA of the concurrent tensor-core stream (0 when mma_n == 0).
+extern "C" int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int mma_n, int mma_count, double *cycles_per_round,
+                               double *cycles_per_mma)
+{
+    using namespace focr;
+    if (!ctx || !cycles_per_round || !cycles_per_mma || nw < 4 || nw > 16 || (nw & 3) || mode < 0 || mode > 3 || iters < 1 ||
+        mma_n < 0 || mma_n > 256 || (mma_n & 15))
+        return focr_internal_fail(FOCR_ERR_ARG, "focr_bench_tmem: bad argument");
+    if (cudaSetDevice(focr_internal_device(ctx)) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
+    long long *d = nullptr;
+    if (cudaMalloc((void **)&d, sms * 16) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
+    const size_t smem = (size_t)7 * 2 * (128 + 256) * 16 + 1024;
+    if (cudaFuncSetAttribute(tmem_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaFuncSetAttribute");
+    tmem_bench_kernel<<<sms, 32 * (nw + 1), smem, st>>>(nw, mode, 8, mma_n, 8, d);
+    tmem_bench_kernel<<<sms, 32 * (nw + 1), smem, st>>>(nw, mode, iters, mma_n, mma_count, d);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, std::string("tmem bench: ") + cudaGetErrorString(e));
+    std::vector<long long> h(sms * 2);
+    cudaMemcpy(h.data(), d, sms * 16, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    std::vector<long long> a(sms), b(sms);
+    for (int i = 0; i < sms; i++) a[i] = h[2 * i], b[i] = h[2 * i + 1];
+    std::sort(a.begin(), a.end());
+    std::sort(b.begin(), b.end());
+    *cycles_per_round = (double)a[sms / 2] / iters;
+    *cycles_per_mma = mma_n > 0 ? (double)b[sms / 2] / ((double)mma_count * 7) : 0.0;
     return FOCR_OK;
 }

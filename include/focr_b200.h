@@ -101,7 +101,9 @@ uint64_t focr_ctx_launch_count(const focr_ctx *ctx);
  * each stage of the pipeline.  focr_ctx_profile_read synchronises, adds up the event intervals
  * recorded since the last read into ms_out[FOCR_STAGE_*] / launches_out[FOCR_STAGE_*] and resets.
  * This is how bench.py measures the correlation kernel's average launch duration live. */
-enum { FOCR_STAGE_INVERT = 0, FOCR_STAGE_STATS = 1, FOCR_STAGE_SCAN = 2, FOCR_STAGE_FINALIZE = 3, FOCR_N_STAGES = 4 };
+/* FOCR_STAGE_EXACT (the exact f64 pass over the tensor-core screen's survivors) is a sub-interval of FOCR_STAGE_SCAN. */
+enum { FOCR_STAGE_INVERT = 0, FOCR_STAGE_STATS = 1, FOCR_STAGE_SCAN = 2, FOCR_STAGE_FINALIZE = 3, FOCR_STAGE_EXACT = 4,
+       FOCR_N_STAGES = 5 };
 int focr_ctx_profile(focr_ctx *ctx, int enable);
 int focr_ctx_profile_read(focr_ctx *ctx, double *ms_out, uint64_t *launches_out);
 
@@ -194,6 +196,14 @@ int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys
  * (MEASURED_PEAKS.json has no integer tensor peak). */
 int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
                        double *ms_total);
+
+double focr_bench_umma_issue_cycles(void);
+
+/* Measurement aid: TMEM <-> register traffic (tcgen05.ld / tcgen05.st 32x32b.x32) from nw warps, optionally
+ * while another warp streams MMAs of N = mma_n; mode 0 = ld, 1 = ld + st, 2 = st, 3 = ld + the screen's max tree.
+ * The correlation kernel's epilogue ceiling. */
+int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int mma_n, int mma_count, double *cycles_per_round,
+                    double *cycles_per_mma);
 
 /* ------------------------------------------------------------------------------------------
  * Section 4 -- C hooks into the C++ host mirror (font-ocr_b200/host/focr_host.hpp), used by tests.
