@@ -298,7 +298,11 @@ def run_ours(args):
                     for w, h, _ in classes}
         ops_dense = sum(2.0 * w * h * c * dense_windows(w, h) for w, h, c in classes) * P * args.steps
         ops_eff = sum(2.0 * w * h * c * dense_windows(w, h) * frac_eff[(w, h)] for w, h, c in classes) * P * args.steps
+        # "scan" = correlation kernel + exact pass over its survivors; the roofline is for the correlation kernel alone
         scan_ms, scan_launches = prof["scan"]
+        exact_ms, exact_launches = prof.get("exact", (0.0, 0))
+        scan_ms -= exact_ms
+        scan_launches -= exact_launches
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -321,7 +325,12 @@ def run_ours(args):
             pass
         traffic = None
         try:  # per-launch DRAM bytes of the correlation kernel from the committed ncu capture
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_tc_traffic.json")))["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_tc_traffic.json")))
+            # per-launch DRAM bytes were captured on a 16-page chunk; scale to this run's average chunk
+            if "dram_bytes_per_page" in tj:
+                traffic = tj["dram_bytes_per_page"] * (P * args.steps * len(classes)) / max(scan_launches, 1)
+            else:
+                traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

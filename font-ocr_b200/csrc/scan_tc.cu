@@ -87,15 +87,17 @@ struct TcParams {
     int n_w, n_h, np;
     int n_hp;          // page rows an output row needs (n_h rounded up to 2 when np == 16)
     int ksteps;        // tcgen05.mma kind::i8 per output row
-    int nb;            // templates per launch = N of the MMAs (multiple of 16)
-    int nunits;        // 32-column epilogue units per accumulator buffer
-    int nbs;           // TMEM column stride between accumulator buffers (nb rounded up to 32)
-    int nbuf;          // accumulator buffers
+    int nb;            // columns per launch = nsub * nbs
+    int nsub;          // sub-blocks: jobs (accumulators) per output row
+    int nunits;        // 32-column epilogue units per accumulator
+    int nbs;           // columns per sub-block = N of the MMAs = TMEM column stride between accumulators (multiple of 32)
+    int nbuf;          // accumulators (even)
+    int nbpp;          // accumulators per pipeline (issuing thread + epilogue team) = nbuf / 2
     int ring;          // expanded-row ring slots = ring_groups * 4
     int ring_groups;
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
-    const uint8_t *btile;     // [2*ksteps][nb][16]
+    const uint8_t *btile;     // [nsub][2*ksteps][nbs][16]
     uint32_t btile_bytes;
     const float2 *colconst;   // [nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
     float thr;
@@ -112,7 +114,6 @@ struct TcParams {
     unsigned int *wd;   // watchdog words (see mbar_wait): [0] raised, [1] tag, [2] info, [3] CTA, [4] warp, [5] parity
     long long *trace;   // timing experiments (env FOCR_TC_TRACE=file): CTA 0's roles add up the cycles they spend in each
                         // wait / phase, [64] (tools/tc_trace.py names the slots)
-    int issuers;        // MMA-issuing threads: 2 (default) or 1 (env FOCR_TC_ISSUERS, experiments)
     int spin;           // bit 0: epilogue polls t_full, bit 1: MMA warps poll t_empty (env FOCR_TC_SPIN, default 3)
     int dbg_mode;       // timing experiments only (env FOCR_TC_DBG, a bit mask; results are wrong when non-zero):
                         // 1 epilogue skips the TMEM reads, 2 epilogue loads but does not screen, 4 no MMAs are issued,
@@ -386,13 +387,15 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const uint32_t idesc8 = (2u << 4)                          // D format: S32
                             | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
                             | (0u << 15) | (0u << 16)          // A, B: K-major
-                            | ((uint32_t)(p.nb >> 3) << 17)    // N
+                            | ((uint32_t)(p.nbs >> 3) << 17)   // N
                             | ((128u >> 4) << 24);             // M = 128
     const uint32_t idesc16 = (1u << 4)                         // D format: F32 (same TMEM columns, read as fp32)
                              | (0u << 7) | (0u << 10)          // A, B: F16
-                             | ((uint32_t)(p.nb >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs;
-    const uint32_t b_lbo16 = ((uint32_t)p.nb * 16u) >> 4, b_inc = 2 * b_lbo16;
+                             | ((uint32_t)(p.nbs >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbpp = p.nbpp, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs,
+                   nsub = p.nsub;
+    const uint32_t b_lbo16 = (uint32_t)p.nbs, b_inc = 2 * b_lbo16;      // 16-byte units: K chunks of B are nbs columns apart
+    const uint32_t b_sub = 2 * ksteps * b_lbo16, b2_sub = 2 * b_lbo16;   // sub-block strides of the B and B2 tiles
     const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
     const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
     const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
@@ -418,17 +421,17 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     uint32_t rel_g = 0, rel_rows = TC_G;     // page-row groups: next to hand back / rows covered once it is
     uint32_t new_g = 0, new_par = 0, rows_ready = 0;
     uint32_t rel2_g = 0, rel2_rows = TC_G, new2_g = 0, new2_par = 0, rows2_ready = 0;
-    const uint32_t step = p.issuers;         // own rows are `step` apart
-    uint32_t buf = mw, bpar = 0, d0 = mw * nbs;   // accumulator of the next own row (row index mod nbuf), its phase, its TMEM column
+    // accumulators of this pipeline: mw, mw+2, ...; job k of the pipeline uses number k mod nbpp
+    uint32_t kb = 0, kpar = 0;               // index of the next job's accumulator within the pipeline, its phase
     bool first_round = true;
     uint32_t o_slot16 = a2_addr16 + mw * (2048u >> 4);   // A2 ring slot address (>> 4) of the next own row
     Item it;
     for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
         const uint32_t n_out_rows = it.ys1 - it.ys0;
-        const uint32_t j0 = step == 2 ? (mw - o_item) & 1u : 0u;   // first own row of the item
+        const uint32_t j0 = (mw - o_item) & 1u;          // first own row of the item
         uint32_t a_first = a_item + j0 * pitch16;        // (a_item < a_end, one slot more never needs two wraps)
         if (a_first >= a_end) a_first -= a_wrap;
-        for (uint32_t j = j0; j < n_out_rows; j += step) {
+        for (uint32_t j = j0; j < n_out_rows; j += 2) {
             const uint32_t o = o_item + j, g_first = g_item + j;
             TC_PROG(1 + mw, (1u << 24) | o);
             // operands: page rows g_first .. g_first+n_hp-1 and the A2 row of this output
@@ -442,40 +445,41 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
                 rows2_ready += TC_G;
                 if (++new2_g == TC_A2_GROUPS) new2_g = 0, new2_par ^= 1;
             }
-            TC_PROG(1 + mw, (2u << 24) | o);
-            if (!first_round) TT(2, mbar_wait(t_empty + buf, bpar ^ 1, p.wd, 16 + mw, o, sm.prog));
-            TC_PROG(1 + mw, (3u << 24) | o);
-            tc_fence_after();
-            const long long ti_ = tron ? clock64() : 0;
-            // F = A2 . B2^T in fp32 (accumulate off).  K = 16 fp16 = two 16-byte chunks: both read the row's
-            // statistics (LBO = 0) and the second chunk of B2 is all zeros.
-            if (corr && mma_on) tc_mma_f16_overwrite(d0, desc_hi | o_slot16, desc_hi | b2_lo, idesc16);
-            // K steps: consecutive ring slots (no wrap inside a row), consecutive B chunks
-            if (KS > 0) {
+            // one job per sub-block: the row's operands are shared, the templates (B, B2) and the accumulator differ
+            uint32_t b_lo = b_lo0, b2 = b2_lo;
+            for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub) {
+                const uint32_t acc = mw + 2 * kb, d0 = acc * nbs;
+                TC_PROG(1 + mw, (2u << 24) | o);
+                if (!first_round) TT(2, mbar_wait(t_empty + acc, kpar ^ 1, p.wd, 16 + mw, o, sm.prog));
+                tc_fence_after();
+                const long long ti_ = tron ? clock64() : 0;
+                // F = A2 . B2^T in fp32 (accumulate off).  K = 16 fp16 = two 16-byte chunks: both read the row's
+                // statistics (LBO = 0) and the second chunk of B2 is all zeros.
+                if (corr && mma_on) tc_mma_f16_overwrite(d0, desc_hi | o_slot16, desc_hi | b2, idesc16);
+                // K steps: consecutive ring slots (no wrap inside a row), consecutive B chunks
+                if (KS > 0) {
 #pragma unroll
-                for (int k = 0; k < KS; k++)
-                    tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo0 + k * b_inc), idesc8,
-                                 (corr || k) ? 1u : 0u);
-            } else {
-                for (uint32_t k = 0; k < ksteps; k++)
-                    tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo0 + k * b_inc), idesc8,
-                                 (corr || k) ? 1u : 0u);
+                    for (int k = 0; k < KS; k++)
+                        tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo + k * b_inc), idesc8,
+                                     (corr || k) ? 1u : 0u);
+                } else {
+                    for (uint32_t k = 0; k < ksteps; k++)
+                        tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo + k * b_inc), idesc8,
+                                     (corr || k) ? 1u : 0u);
+                }
+                if (tron) tacc[3] += clock64() - ti_;
+                TT(4, tc_commit(t_full + acc));   // accumulator ready for the epilogue
+                if (++kb == nbpp) kb = 0, kpar ^= 1, first_round = false;
             }
-            if (tron) tacc[3] += clock64() - ti_;
-            TC_PROG(1 + mw, (4u << 24) | o);
-            TT(4, tc_commit(t_full + buf));   // accumulator ready for the epilogue
-            TC_PROG(1 + mw, (5u << 24) | o);
             // bookkeeping for the next own row (off the critical path: the tensor pipe is busy with this row)
-            buf += step, d0 += step * nbs;
-            if (buf >= nbuf) buf -= nbuf, d0 -= nbuf * nbs, bpar ^= 1, first_round = false;
-            o_slot16 += step * (2048u >> 4);
+            o_slot16 += 2 * (2048u >> 4);
             if (o_slot16 >= a2_end16) o_slot16 -= a2_wrap16;
-            a_first += step * pitch16;
+            a_first += 2 * pitch16;
             if (a_first >= a_end) a_first -= a_wrap;
             // hand back every group that lies entirely below what the next own output reads (at the end of an
             // item that is the next item's first own row, whichever it is: use its first row)
-            const uint32_t g_next = j + step < n_out_rows ? g_first + step : g_item + n_out_rows + n_hp - 1;
-            const uint32_t o_next = j + step < n_out_rows ? o + step : o_item + n_out_rows;
+            const uint32_t g_next = j + 2 < n_out_rows ? g_first + 2 : g_item + n_out_rows + n_hp - 1;
+            const uint32_t o_next = j + 2 < n_out_rows ? o + 2 : o_item + n_out_rows;
             while (rel_rows <= g_next) {
                 TT(4, tc_commit(a_empty + rel_g));
                 rel_rows += TC_G;
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint8_t *raw = ring + (size_t)(p.ring + p.n_hp) * p.row_pitch;  // + mirror slots: slot ring+i repeats slot i (i < n_hp-1)
     uint8_t *a2ring = raw + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127);  // [TC_A2_GROUPS*4][128][16 B] fp16 x 8
     uint8_t *b2tile = a2ring + TC_A2_GROUPS * TC_G * 2048;                // [2][nb][16 B]: chunk 0 constants, chunk 1 zeros
-    uint64_t *bars = (uint64_t *)(b2tile + (size_t)2 * p.nb * 16);
+    uint64_t *bars = (uint64_t *)(b2tile + (size_t)2 * p.nb * 16);   // b2tile: [nsub][2][nbs][16]
     uint64_t *bar_btile = bars;                       // 1
     uint64_t *raw_full = bars + 1;                    // TC_RAW_GROUPS
     uint64_t *raw_empty = raw_full + TC_RAW_GROUPS;   // TC_RAW_GROUPS
@@ -532,11 +536,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
             mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, p.issuers);     // one tcgen05.commit per MMA-issuing thread
+            mbar_init(a_empty + i, 2);     // one tcgen05.commit per MMA-issuing thread
         }
         for (int i = 0; i < TC_A2_GROUPS; i++) {
             mbar_init(a2_full + i, 4);     // one arrival per A2 warp
-            mbar_init(a2_empty + i, p.issuers);
+            mbar_init(a2_empty + i, 2);
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
@@ -554,8 +558,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const __half a2 = __float2half_rn(a - __half2float(a1)), b2 = __float2half_rn(b - __half2float(b1));
         const __half big = __float2half_rn(-TC_BIG), padh = __float2half_rn(pad ? -TC_BIG : 510.f);
         __align__(16) __half h[8] = {__hneg(b1), __hneg(b2), __hneg(b1), __hneg(a1), __hneg(a2), __hneg(a1), big, padh};
-        *(uint4 *)(b2tile + (size_t)t * 16) = *(const uint4 *)h;
-        *(uint4 *)(b2tile + ((size_t)p.nb + t) * 16) = make_uint4(0, 0, 0, 0);
+        const int sb = t / p.nbs, n = t - sb * p.nbs;      // layout [sub][K chunk][column][16 B]
+        uint8_t *dst = b2tile + ((size_t)sb * 2 * p.nbs + n) * 16;
+        *(uint4 *)dst = *(const uint4 *)h;
+        *(uint4 *)(dst + (size_t)p.nbs * 16) = make_uint4(0, 0, 0, 0);
     }
     if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
@@ -620,7 +626,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         if (lane == 0) TT_END(32);
     } else if (warp == 1 || warp == 2) {
         // ================================================================== MMA issuers (tc_mma_role)
-        if ((int)warp <= p.issuers && elect_one()) {
+        if (elect_one()) {
             TcSmem sm = {btile, ring, a2ring, b2tile, bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty, prog};
             const uint32_t mw = warp - 1;
             switch (p.ksteps) {
@@ -747,27 +753,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const int team = (e >> 2) & 1, sub = e >> 3;
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t nbuf = p.nbuf;
+        const uint32_t nbpp = p.nbpp, nsub = p.nsub;
         const int nunits = p.nunits;
         const float T = p.dbg_acc ? 3.0e38f : TC_C0 - TC_MARGIN;
-        uint32_t buf = team, bpar = 0;            // accumulator of this team's next row (row index mod nbuf) and its phase
+        uint32_t kb = 0, kpar = 0;                // the team's next job: accumulator team + 2*kb, phase kpar (as in tc_mma_role)
         Hit *my_list = p.cands + (size_t)(blockIdx.x * TC_LISTS_PER_CTA + e) * p.cand_cap;
         uint32_t my_count = 0;
         uint32_t orow0 = 0;                       // global output-row index of the current item's first row
         const bool no_ld = TC_EXP && (p.dbg_mode & 1), no_screen = TC_EXP && (p.dbg_mode & 2);
+        const int dbg_sub = p.dbg_acc ? p.dbg_col / p.nbs : -1, dbg_c = p.dbg_acc ? p.dbg_col % p.nbs : 0;
         TT_BEGIN();
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int gx = it.x0 + m;
             for (int y = it.ys0 + (int)((team - orow0) & 1u); y < it.ys1; y += 2) {
+              for (uint32_t sb = 0; sb < nsub; sb++) {
+                const uint32_t acc = team + 2 * kb;
                 if (lane == 0) TC_PROG(warp, (uint32_t)(y - it.ys0) + orow0);
-                TT(0, mbar_wait(t_full + buf, bpar, p.wd, 20 + team, y, prog));
+                TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + team, y, prog));
                 tc_fence_after();
-                const uint32_t tb = tlane + buf * p.nbs;
-                auto release = [&]() {  // every tcgen05.ld of this row has completed: hand the accumulator back
+                const uint32_t tb = tlane + acc * p.nbs;
+                const uint32_t cbase = p.col_base + sb * p.nbs;
+                auto release = [&]() {  // every tcgen05.ld of this job has completed: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + buf);
+                    if (lane == 0) mbar_arrive(t_empty + acc);
                 };
                 auto screen = [&](uint32_t (&v)[32], int u) {
                     float t[11];
@@ -788,11 +798,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= T ? 1u : 0u) << j;
-                        append_candidates(my_list, p.cand_cap, my_count, mask, p.col_base + u * 32, it.page, gx, y);
+                        append_candidates(my_list, p.cand_cap, my_count, mask, cbase + u * 32, it.page, gx, y);
                     }
                 };
-                if (p.dbg_acc && sub == 0) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
-                    const uint32_t a = tc_ld1(tb + p.dbg_col);
+                if (p.dbg_acc && sub == 0 && (int)sb == dbg_sub) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
+                    const uint32_t a = tc_ld1(tb + dbg_c);
                     tc_wait_ld();
                     if (gx >= 1 && gx <= p.r_w - p.n_w) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
                 }
@@ -824,8 +834,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                         if (h3) screen(vb, u3);
                     }
                 }
-                buf += 2;
-                if (buf >= nbuf) buf -= nbuf, bpar ^= 1;
+                if (++kb == nbpp) kb = 0, kpar ^= 1;
+              }
             }
             orow0 += it.ys1 - it.ys0;
         }
@@ -854,7 +864,8 @@ struct CandArgs {
     const unsigned int *cand_count;  // [n_lists]
     unsigned int *cand_max;  // high-water mark of a list's count (overflow detection on the host)
     const uint32_t *tpl_of;  // [n_blocks*nb] bank index per class column (0xFFFFFFFF = padding)
-    const uint8_t *rows;     // [n_tpl][n_h][np] zero-padded template rows of the class (column i == template i)
+    const uint32_t *cls_of;  // [n_blocks*nb] index of the column's template within `rows`
+    const uint8_t *rows;     // [n_tpl][n_h][np] zero-padded template rows of the class
     const TplInfo *tpl;
     const uint8_t *inv;
     size_t inv_page_stride;
@@ -880,7 +891,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             const uint32_t y = c.yx >> 16, x = c.yx & 0xFFFFu;
             // exact numerator: u8 x u8 -> u32 with __dp4a on byte-shifted page words; the template rows are
             // zero padded to np bytes, so bytes beyond n_w contribute nothing
-            const uint32_t *trow = (const uint32_t *)(a.rows + (size_t)c.t * a.n_h * a.np);
+            const uint32_t *trow = (const uint32_t *)(a.rows + (size_t)a.cls_of[c.t] * a.n_h * a.np);
             const uint8_t *p0 = a.inv + (size_t)c.page * a.inv_page_stride + (size_t)y * a.pitch + x;
             const int sh = (int)((uintptr_t)p0 & 3) * 8, nw4 = a.np >> 2;
             const uint32_t *prow = (const uint32_t *)((uintptr_t)p0 & ~(uintptr_t)3);
@@ -943,39 +954,53 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     if (ring_groups > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
     // the fp16 statistics operand needs s_p <= 255*n <= 65504 (fp16 range); larger boxes take the SIMT kernel
     if (n_w * n_h > 256) return 0;
-    // largest NB (multiple of 16, <= 256) whose B tile fits next to the rings
+    // largest column count per launch (multiple of 32, <= 256) whose B tiles fit next to the rings
     int nb_max = 256;
     while (nb_max >= 32 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)n_hp, row_pitch, nb_max) > TC_SMEM_BUDGET) nb_max -= 32;
     if (nb_max < 32) return 0;
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
-    // a multiple of 32: the epilogue works in 32-column units and every column of a unit must be written by the
-    // MMA (padding columns carry B2 pad = BIG and can never survive the screen)
-    tc.nb = ((n_tpl + tc.n_blocks - 1) / tc.n_blocks + 31) & ~31u;
-    const size_t tile = (size_t)2 * tc.ksteps * tc.nb * 16;
+    const uint32_t per_blk = (n_tpl + tc.n_blocks - 1) / tc.n_blocks;   // templates per launch
+    // Sub-blocks: a launch may split its columns into accumulator-sized groups that share the row's operands (one job per
+    // group and row), which gives each issuing thread / epilogue team two accumulators even for wide banks.  Measured
+    // (B200, 222 templates): 2 x 128 columns is SLOWER than 1 x 224 (0.465 vs 0.417 ms/page) -- the cost of a job is set by
+    // the control threads' instruction streams, not by the MMAs -- so the split is only taken on request
+    // (FOCR_TC_SPLIT=1, experiments).  Column counts are multiples of 32: the epilogue works in 32-column units and every
+    // column of a unit must be written by the MMA (padding columns carry -BIG in B2 and can never survive the screen).
+    tc.nsub = (per_blk > 128 && getenv("FOCR_TC_SPLIT")) ? 2 : 1;
+    const uint32_t per_sub = (per_blk + tc.nsub - 1) / tc.nsub;
+    tc.nbsub = (per_sub + 31) & ~31u;
+    tc.nb = tc.nsub * tc.nbsub;
+    const size_t subtile = (size_t)2 * tc.ksteps * tc.nbsub * 16, tile = subtile * tc.nsub;
     std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
     std::vector<float2> cst((size_t)tc.n_blocks * tc.nb);
-    std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
+    std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu), cof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
     const float inf = INFINITY;
     for (auto &c : cst) c = make_float2(inf, 0.f);
     tc.blk_bmax.assign(tc.n_blocks, 0.f);
     tc.blk_normmax.assign(tc.n_blocks, 0.f);
+    tc.col_of.assign(n_tpl, 0);
     for (uint32_t i = 0; i < n_tpl; i++) {
-        const uint32_t blk = i / tc.nb, n = i % tc.nb;
+        const uint32_t blk = i / per_blk, r = i % per_blk, sub = r / per_sub, n = r % per_sub;
+        const uint32_t col = sub * tc.nbsub + n;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
             const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
-            memcpy(&bt[blk * tile + ((size_t)kc * tc.nb + n) * 16], rows_host + ((size_t)i * n_h + row) * np + boff, 16);
+            memcpy(&bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16], rows_host + ((size_t)i * n_h + row) * np + boff, 16);
         }
         const TplInfo &ti = info[i];
         // norm_n = sqrt(s2_n - s_n^2/n) = 1/rnorm_n ; constant (incl. all-zero) templates can never hit
         const double norm_n = 1.0 / ti.rnorm_n;
         const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
-        cst[(size_t)blk * tc.nb + n] = make_float2(ok ? (float)norm_n : inf, (float)(ti.s_n * ti.n_recip));
-        tof[(size_t)blk * tc.nb + n] = bank_index[i];
+        cst[(size_t)blk * tc.nb + col] = make_float2(ok ? (float)norm_n : inf, (float)(ti.s_n * ti.n_recip));
+        tof[(size_t)blk * tc.nb + col] = bank_index[i];
+        cof[(size_t)blk * tc.nb + col] = i;
+        tc.col_of[i] = blk * tc.nb + col;
         if (ok) {
             tc.blk_bmax[blk] = std::max(tc.blk_bmax[blk], (float)(ti.s_n * ti.n_recip));
             tc.blk_normmax[blk] = std::max(tc.blk_normmax[blk], (float)norm_n);
         }
     }
+    if (cudaMalloc(&tc.cls_of, cof.size() * 4) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.cls_of, cof.data(), cof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.b_tiles, bt.size()) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.consts, cst.size() * sizeof(float2)) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.tpl_of, tof.size() * 4) != cudaSuccess) return -1;
@@ -991,6 +1016,8 @@ void tc_class_release(TcClass &tc)
     if (tc.b_tiles) cudaFree(tc.b_tiles);
     if (tc.consts) cudaFree(tc.consts);
     if (tc.tpl_of) cudaFree(tc.tpl_of);
+    if (tc.cls_of) cudaFree(tc.cls_of);
+    tc.cls_of = nullptr;
     tc.b_tiles = nullptr;
     tc.consts = nullptr;
     tc.tpl_of = nullptr;
@@ -1017,12 +1044,14 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
     p.ksteps = tc.ksteps;
     p.nb = tc.nb;
-    p.nunits = (tc.nb + 31) / 32;
-    p.nbs = (tc.nb + 31) & ~31;
+    p.nsub = tc.nsub;
+    p.nbs = tc.nbsub;
+    p.nunits = tc.nbsub / 32;
     // An EVEN number of accumulators: with two issuing threads / two epilogue teams on alternate rows, accumulator b is then
     // always written by thread b%2 and read by team b%2, so each of them sees every phase of its barriers.  (With an odd
     // count the owners alternate, a waiter can fall two phases behind and the parity test aliases.)
     p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF) & ~1;
+    p.nbpp = p.nbuf / 2;
     p.ring_groups = (p.n_hp + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;  // rows y..y+n_hp-1 may straddle one more group
     p.ring = p.ring_groups * TC_G;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
@@ -1050,12 +1079,11 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     const int items = n_pages * p.n_xstrips * p.n_ysegs;
     const int grid = std::min(items, sm_count);
     p.dbg_acc = dbg_acc;
-    p.dbg_col = dbg_acc ? dbg_pos % (int)tc.nb : -1;
+    const uint32_t dbg_colidx = dbg_acc ? tc.col_of[dbg_pos] : 0;   // dbg_pos = template index within the class
+    p.dbg_col = dbg_acc ? (int)(dbg_colidx % tc.nb) : -1;
     {
         const char *dm = getenv("FOCR_TC_DBG");
         p.dbg_mode = dm ? atoi(dm) : 0;
-        const char *is = getenv("FOCR_TC_ISSUERS");  // honoured in every build: 1 = a single issuing thread
-        p.issuers = is && atoi(is) == 1 ? 1 : 2;
         const char *sp = getenv("FOCR_TC_SPIN");
         p.spin = sp ? atoi(sp) : 3;
     }
@@ -1066,7 +1094,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     }
     const char *trace_path = dbg_acc ? nullptr : getenv("FOCR_TC_TRACE");
         for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
-        if (dbg_acc && blk != (uint32_t)dbg_pos / tc.nb) continue;
+        if (dbg_acc && blk != dbg_colidx / tc.nb) continue;
         if (trace_path && cudaMalloc((void **)&p.trace, (size_t)64 * 8) == cudaSuccess)
             cudaMemsetAsync(p.trace, 0, (size_t)64 * 8, st);
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
@@ -1126,6 +1154,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
         ca.cand_count = a.cand_count;
         ca.cand_max = a.cand_max;
         ca.tpl_of = tc.tpl_of;
+        ca.cls_of = tc.cls_of;
         ca.rows = a.cls.rows;
         ca.tpl = a.tpl;
         ca.inv = a.inv;

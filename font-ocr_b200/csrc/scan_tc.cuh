@@ -14,13 +14,17 @@ struct TcClass {
     bool supported = false;
     uint32_t n_w = 0, n_h = 0, np = 0;
     uint32_t n_tpl = 0;     // real templates of this class
-    uint32_t nb = 0;        // templates per N-block (multiple of 16, <= 256)
-    uint32_t n_blocks = 0;  // N-blocks
+    uint32_t nb = 0;        // columns per launch = nsub * nbsub
+    uint32_t nsub = 0;      // sub-blocks per launch: every output row is nsub jobs (one accumulator each) sharing its operands
+    uint32_t nbsub = 0;     // columns per sub-block = N of the MMAs (multiple of 32, <= 128 when nsub > 1)
+    uint32_t n_blocks = 0;  // launches per chunk of pages
     uint32_t kchunks = 0;   // 16-byte K chunks per template = n_h * np/16
     uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
     uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]
     float2 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
     uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
+    uint32_t *cls_of = nullptr;   // device [n_blocks*nb] index within the class's template rows (0xFFFFFFFF for padding)
+    std::vector<uint32_t> col_of; // host, per class-local template: its column (launch * nb + column)
     std::vector<float> blk_bmax, blk_normmax;  // host, per N-block: max s_n/n and max norm_n over its real columns
 };
 
