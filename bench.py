@@ -285,6 +285,33 @@ def run_ours(args):
     chk_counts = counts_dev.cpu().numpy().view(np.uint32).reshape(P, T)
     assert np.array_equal(chk_counts, counts_np), "device-resident and e2e paths disagree"
 
+    # SURVEY 8f rank 1 (reported beside the headline, not part of it): process_hits on the device, on the match lists
+    # the scan left in HBM, timed with CUDA events on the library's stream including the D2H of the surviving lines;
+    # next to it the C++ host mirror of the same function on the first page's hits
+    post = None
+    if rank == 0:
+        try:
+            letters = bank_h.letters()
+            for _ in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                lp, ls, st_, sm_ = ncc.process_hits_device(ctx, out_dev.data_ptr(), counts_dev.data_ptr(), T, N_OUT, P, letters,
+                                                           0.95, 5, raw=True)
+                e1.record(stream)
+                e1.synchronize()
+            lines = ncc.process_hits_device(ctx, out_dev.data_ptr(), counts_dev.data_ptr(), T, N_OUT, P, letters, 0.95, 5,
+                                            only_page=0)
+            t0 = time.perf_counter()
+            host_lines = ncc.host_process_hits(ncc.get_hits(out_np[0], counts_np[0], letters), 0.95, 5)
+            t_host = time.perf_counter() - t0
+            assert ncc.lines_to_text(host_lines) == ncc.lines_to_text(lines[0])
+            post = {"kernel": "focr_process_hits_device (ncc.rs:723-786)", "ms_per_page": e0.elapsed_time(e1) / P,
+                    "note": "device time of the call per page (6 small kernels + CUB radix sort / scans + D2H of the surviving hits)",
+                    "lines_per_page": len(lp) / float(P), "survivors_per_page": len(st_) / float(P),
+                    "host_mirror_ms_per_page": 1e3 * t_host, "host_mirror": "C++ process_hits via ctypes incl. marshalling, 1 page"}
+        except Exception as ex:  # never let the extra measurement break the bench line
+            post = {"error": str(ex)[:200]}
+
     total_pages = P * world
     value = total_pages * args.steps / (ms_dev / 1e3)
     e2e_value = total_pages * args.steps / (ms_e2e / 1e3)
@@ -360,6 +387,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(out_pin.numel() + counts_pin.numel() * 4) * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "process_hits_device": post,
         }
     bank.close()
     ctx.close()

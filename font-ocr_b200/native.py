@@ -23,7 +23,7 @@ SYMBOLS = [
     "focr_ctx_create", "focr_ctx_destroy", "focr_ctx_set_kernel", "focr_ctx_stream", "focr_ctx_sync",
     "focr_ctx_launch_count", "focr_ctx_profile", "focr_ctx_profile_read",
     "focr_bank_create", "focr_bank_destroy", "focr_bank_size",
-    "focr_ncc_scan", "focr_ncc_scan_device", "focr_window_stats", "focr_ncc_numerators",
+    "focr_ncc_scan", "focr_ncc_scan_device", "focr_process_hits_device", "focr_window_stats", "focr_ncc_numerators",
     "focr_glyph_bank_create", "focr_glyph_bank_destroy", "focr_decode_pages", "focr_sum_of_squares",
     "focr_host_process_hits", "focr_host_search_c_u8", "focr_bench_umma_i8", "focr_bench_umma_issue_cycles", "focr_bench_tmem",
 ]
@@ -78,6 +78,7 @@ def lib():
     l.focr_glyph_bank_destroy.restype = None
     l.focr_decode_pages.argtypes = [vp, vp, vp, sz] + [u32] * 10 + [vp, vp, vp, vp]
     l.focr_sum_of_squares.argtypes = [vp, vp, vp, sz, u32, vp]
+    l.focr_process_hits_device.argtypes = [vp, vp, vp, u32, u32, u32, C.c_float, C.c_int32, u32, u32, vp, vp, vp, vp, vp, vp]
     l.focr_bench_umma_i8.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     l.focr_bench_umma_issue_cycles.restype = C.c_double
     l.focr_bench_tmem.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]

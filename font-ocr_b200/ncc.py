@@ -211,6 +211,40 @@ def process_hits(all_hits, anchor_threshold: float = 0.95, overlap: int = 5):
     return lines
 
 
+def process_hits_device(ctx, matches_dev, counts_dev, T: int, n_out: int, n_pages: int, letters,
+                        anchor_threshold: float = 0.95, overlap: int = 5, raw: bool = False, only_page=None):
+    """process_hits (ncc.rs:723-786) on the GPU, on match lists that are still resident in HBM (the buffers
+    scan_pages_device filled).  Returns, per page, the same lines of (letter, x, y, similarity) tuples as
+    process_hits(get_hits(...)); a page without any anchor line gets [] (the reference panics there, ncc.rs:1040).
+    raw=True returns the C arrays (line_page, line_start, sel_tpl, sel) instead; only_page unpacks one page only."""
+    n_lines, n_sel = np.zeros(1, np.uint32), np.zeros(1, np.uint32)
+    line_cap, sel_cap = 4096 * n_pages, 65536 * n_pages
+    while True:
+        line_page = np.zeros(line_cap, np.uint32)
+        line_start = np.zeros(line_cap + 1, np.uint32)
+        sel_tpl = np.zeros(sel_cap, np.uint32)
+        sel = np.zeros(sel_cap, MATCH_DTYPE)
+        rc = lib().focr_process_hits_device(ctx._h, ptr(matches_dev), ptr(counts_dev), T, n_out, n_pages,
+                                            C.c_float(anchor_threshold), overlap, line_cap, sel_cap, ptr(n_lines), ptr(n_sel),
+                                            ptr(line_page), ptr(line_start), ptr(sel_tpl), ptr(sel))
+        if rc == native.FOCR_ERR_NOMEM and (n_lines[0] > line_cap or n_sel[0] > sel_cap):
+            line_cap, sel_cap = max(line_cap, int(n_lines[0])), max(sel_cap, int(n_sel[0]))
+            continue
+        check(rc)
+        break
+    nl, ns = int(n_lines[0]), int(n_sel[0])
+    if raw:
+        return line_page[:nl], line_start[:nl + 1], sel_tpl[:ns], sel[:ns]
+    pages = [[] for _ in range(n_pages)]
+    for l in range(nl):
+        if only_page is not None and int(line_page[l]) != only_page:
+            continue
+        a, b = int(line_start[l]), int(line_start[l + 1])
+        pages[int(line_page[l])].append([(letters[int(sel_tpl[k])], int(sel[k]["x"]), int(sel[k]["y"]),
+                                          np.float32(sel[k]["similarity"])) for k in range(a, b)])
+    return pages
+
+
 def lines_to_text(lines):
     return ["".join(h[0] for h in line) for line in lines]
 

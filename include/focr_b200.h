@@ -185,6 +185,23 @@ int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t 
                       uint32_t max_cells, uint16_t *glyphs_host, uint32_t *n_cells_host,
                       uint32_t *line_y_host, uint32_t *n_lines_host);
 
+/* Device-side process_hits (ncc.rs:723-786 with partition_by, ncc.rs:1036-1052) for a batch of pages whose match
+ * lists are still resident in HBM -- the out_dev / counts_dev buffers focr_ncc_scan_device filled (template order =
+ * the reference's get_hits order, ncc.rs:675-681).  Anchor filter, the two stable sorts (as one radix sort by
+ * (page, y, x, get_hits position)), first-element-anchored overlap groups and the last-maximum pick all run on the GPU;
+ * only the surviving hits come back:
+ *   line_page_host[l]    page of output line l (lines are ordered by page, then y; every distinct y is a line)
+ *   line_start_host[l]   index of the line's first survivor in sel_* (n_lines + 1 entries)
+ *   sel_tpl_host[k], sel_host[k]   bank template index and {x, y, similarity} of survivor k, x ascending in a line
+ * n_lines_out / n_sel_out always receive the sizes; if line_cap or sel_cap is too small the call returns
+ * FOCR_ERR_NOMEM and the caller retries with larger arrays.  A page without any anchor line simply has no lines here
+ * (the reference panics in partition_by, ncc.rs:1040; the host mirrors keep that behaviour).  At most 1024 pages per call,
+ * T * n_out <= 2^22. */
+int focr_process_hits_device(focr_ctx *ctx, const focr_match *matches_dev, const uint32_t *counts_dev, uint32_t T,
+                             uint32_t n_out, uint32_t n_pages, float anchor_threshold, int32_t overlap, uint32_t line_cap,
+                             uint32_t sel_cap, uint32_t *n_lines_out, uint32_t *n_sel_out, uint32_t *line_page_host,
+                             uint32_t *line_start_host, uint32_t *sel_tpl_host, focr_match *sel_host);
+
 /* main.rs:510-516 `sum_of_squares` for n_pairs pairs of equal-length strips (parity probe; the
  * decode kernel uses the algebraically identical Sum(ref^2) - 2*dot + Sum(g^2) form). */
 int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys_host, size_t len,

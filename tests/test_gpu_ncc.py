@@ -205,3 +205,44 @@ def test_cpp_host_searcher_matches_golden(ctx, golden):
         assert got.tobytes() == golden["text16_hits"][off:off + n].tobytes(), t
     with pytest.raises(NotImplementedError):
         ncc.host_search_c_u8(golden["text16_page"], np.zeros((5, 17), np.uint8), 0.8)
+
+
+def test_process_hits_on_device(ctx, oracle, font, pkg):
+    """process_hits (ncc.rs:723-786) on the GPU, on match lists that never leave HBM, against
+    the oracle's restatement and the host mirrors: identical lines (letters, coordinates, f32 scores, order),
+    including duplicate lines at y+-1, ties, and a page without any anchor line."""
+    import torch
+    from font_ocr_b200 import native, ncc
+
+    bank_h = pkg.raster.TemplateBank(font, 13, x_bits=1)
+    tpls = [t.pixels for t in bank_h.templates]
+    letters = bank_h.letters()
+    T, n_out = len(tpls), 1024
+    pages = np.stack([pkg.pages.make_ncc_page(bank_h, 608, 400, seed=s, shifts="bank")[0] for s in range(3)] +
+                     [np.full((400, 608), 255, np.uint8)])  # the last page is blank: no hits, no lines
+    P = len(pages)
+    bank = ncc.Bank(ctx, tpls)
+    dev = torch.from_numpy(pages).cuda()
+    out_dev = torch.zeros(P * T * n_out * 8, dtype=torch.uint8, device="cuda")
+    cnt_dev = torch.zeros(P * T, dtype=torch.int32, device="cuda")
+    ncc.scan_pages_device(ctx, bank, dev.data_ptr(), 608 * 400, 608, 608, 400, P, 0.8, n_out, out_dev.data_ptr(),
+                          cnt_dev.data_ptr())
+    ctx.sync()
+    m = out_dev.cpu().numpy().view(native.MATCH_DTYPE).reshape(P, T, n_out)
+    c = cnt_dev.cpu().numpy().view(np.uint32).reshape(P, T)
+    for anchor, overlap in ((0.95, 5), (0.9, 0), (0.99, 40)):
+        got = ncc.process_hits_device(ctx, out_dev.data_ptr(), cnt_dev.data_ptr(), T, n_out, P, letters, anchor, overlap)
+        assert len(got) == P
+        for p in range(P):
+            hits = ncc.get_hits(m[p], c[p], letters)
+            try:
+                exp = oracle.process_hits(hits, anchor, overlap)
+            except IndexError:  # the reference panics when no line has an anchor (ncc.rs:1040)
+                exp = []
+            assert len(got[p]) == len(exp), (anchor, overlap, p, len(got[p]), len(exp))
+            for gl, el in zip(got[p], exp):
+                assert [(h[0], h[1], h[2], np.float32(h[3]).tobytes()) for h in gl] == \
+                       [(h[0], h[1], h[2], np.float32(h[3]).tobytes()) for h in el], (anchor, overlap, p)
+        assert got[P - 1] == []
+    assert any(len(lines) > 0 for lines in got)
+    bank.close()
