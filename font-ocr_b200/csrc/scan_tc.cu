@@ -657,8 +657,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         TT_BEGIN();
         for (uint32_t g0 = 0; g0 < total_rows; g0 += TC_G) {
             if (lane == 0) TC_PROG(warp, g0);
-            TT(0, mbar_wait(raw_full + rg, rgpar, p.wd, 2, g0, prog));
-            if (!first_round) TT(1, mbar_wait(a_empty + ag, agpar, p.wd, 3, g0, prog));
+            if (w == 0) {  // one warp polls, the other three wait on a named barrier (see the epilogue)
+                TT(0, mbar_wait(raw_full + rg, rgpar, p.wd, 2, g0, prog));
+                if (!first_round) TT(1, mbar_wait(a_empty + ag, agpar, p.wd, 3, g0, prog));
+            }
+            asm volatile("bar.sync 3, 128;" ::: "memory");
             if (g0 + w < total_rows && !(TC_EXP && (p.dbg_mode & 16))) {
                 const uint32_t *rw = (const uint32_t *)(raw + (rg * TC_G + w) * TC_RAW_BYTES);
                 const uint32_t s = ag * TC_G + w;
@@ -704,7 +707,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         TT_BEGIN();
         for (uint32_t o0 = 0; o0 < total_out; o0 += TC_G) {
             if (lane == 0) TC_PROG(warp, o0);
-            if (!first_round) TT(0, mbar_wait(a2_empty + ag, agpar, p.wd, 4, o0, prog));
+            if (!first_round) {
+                if (w == 0) TT(0, mbar_wait(a2_empty + ag, agpar, p.wd, 4, o0, prog));
+                asm volatile("bar.sync 4, 128;" ::: "memory");
+            }
             const uint32_t o = o0 + w;
             if (o < total_out) {
                 while (have && o >= item_o0 + (uint32_t)(it.ys1 - it.ys0)) {  // advance to the item that owns row o
@@ -786,7 +792,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
               for (uint32_t sb = 0; sb < nsub; sb++) {
                 const uint32_t acc = pipe + 2 * kb;
                 if (lane == 0) TC_PROG(warp, (uint32_t)(y - it.ys0) + orow0);
-                TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
+                // ONE warp of the team polls the mbarrier (polling costs shared-memory bandwidth, which the tensor core's
+                // operand reads already use to ~80 %); its team-mates wait on a hardware named barrier
+                if (TC_TEAMS == 2) {
+                    if (e == team * 4) TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
+                    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
+                } else {
+                    TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
+                }
                 tc_fence_after();
                 const uint32_t tb = tlane + acc * p.nbs;
                 const uint32_t cbase = p.col_base + sb * p.nbs;
