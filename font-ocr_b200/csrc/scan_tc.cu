@@ -166,19 +166,29 @@ __device__ uint32_t g_wdprog[32];
 // Watchdog: a wait that has timed out ~8000 times (>= 0.15 s) records who is stuck (wd[1..4] = tag, info, CTA,
 // warp) and raises wd[0]; every waiting thread that sees wd[0] gives up, so a protocol bug ends the kernel with an
 // error the host reports instead of hanging the GPU.
+template <bool HINT = true>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
                                           uint32_t info = 0, volatile uint32_t *prog = nullptr)
 {
     const uint32_t addr = smem_u32(bar);
     uint32_t done, tries = 0;
     for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity), "r"(20000u)
-            : "memory");
+        if (HINT)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity), "r"(20000u)
+                : "memory");
+        else  // accumulator hand-offs: try_wait without a suspend-time hint answers ~30 cycles sooner (tools/pingpong.py)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(addr), "r"(parity)
+                : "memory");
         if (done) return;
         if (wd && (++tries & 63u) == 0) {
             if (tries == 4096u && prog && atomicCAS(wd + 6, 0u, 1u) == 0u) {  // first long wait anywhere: snapshot of the CTA's progress
@@ -457,7 +467,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
             for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub) {
                 const uint32_t acc = mw + 2 * kb, d0 = acc * nbs;
                 TC_PROG(1 + mw, (2u << 24) | o);
-                if (!first_round) TT(2, mbar_wait(t_empty + acc, kpar ^ 1, p.wd, 16 + mw, o, sm.prog));
+                if (!first_round) TT(2, mbar_wait<false>(t_empty + acc, kpar ^ 1, p.wd, 16 + mw, o, sm.prog));
                 tc_fence_after();
                 const long long ti_ = tron ? clock64() : 0;
                 // F = A2 . B2^T in fp32 (accumulate off).  K = 16 fp16 = two 16-byte chunks: both read the row's
@@ -795,7 +805,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 // ONE warp of the team polls the mbarrier (polling costs shared-memory bandwidth, which the tensor core's
                 // operand reads already use to ~80 %); its team-mates wait on a hardware named barrier
                 if (TC_TEAMS == 2) {
-                    if (e == team * 4) TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
+                    if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
                 } else {
                     TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));

@@ -205,7 +205,65 @@ __global__ void __launch_bounds__(32 * 17, 1) tmem_bench_kernel(int nw, int mode
     }
 }
 
+// Hand-shake round trip: one thread signals barrier A (tcgen05.commit or a plain arrive), a whole warp waits for A and
+// its lane 0 arrives on barrier B, the first thread waits for B -- `iters` times.  wait_kind 0 = mbarrier.try_wait with a
+// 20 us suspend hint (what scan_tc.cu uses), 1 = try_wait without hint, 2 = test_wait polling.  nwait = waiting warps.
+__device__ __forceinline__ void pp_wait(uint32_t addr, uint32_t parity, int kind)
+{
+    uint32_t done;
+    do {
+        if (kind == 0)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        else if (kind == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__global__ void __launch_bounds__(32 * 9, 1) pingpong_kernel(int wait_kind, int use_commit, int nwait, int iters, long long *out)
+{
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ub_smem_u32(&bars[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ub_smem_u32(&bars[1])), "r"(nwait) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ub_smem_u32(&tmem_ptr)), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t a = ub_smem_u32(&bars[0]), b = ub_smem_u32(&bars[1]);
+    if (warp == 0) {
+        if (lane == 0) {
+            const long long t0 = clock64();
+            for (int it = 0; it < iters; it++) {
+                if (use_commit)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(a) : "memory");
+                else
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+                pp_wait(b, it & 1, wait_kind);
+            }
+            out[blockIdx.x] = clock64() - t0;
+        }
+    } else if (warp <= nwait) {
+        for (int it = 0; it < iters; it++) {
+            pp_wait(a, it & 1, wait_kind);
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_ptr), "r"(32) : "memory");
+}
+
 }  // namespace focr
+
 
 static double g_last_issue_cycles = 0;
 // cycles (median over SMs) the issuing thread of the last focr_bench_umma_i8 run needed to get past its last
@@ -283,5 +341,28 @@ extern "C" int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int m
     std::sort(b.begin(), b.end());
     *cycles_per_round = (double)a[sms / 2] / iters;
     *cycles_per_mma = mma_n > 0 ? (double)b[sms / 2] / ((double)mma_count * 7) : 0.0;
+    return FOCR_OK;
+}
+
+// cycles per hand-shake round trip (see pingpong_kernel), median over SMs
+extern "C" int focr_bench_pingpong(focr_ctx *ctx, int wait_kind, int use_commit, int nwait, int iters, double *cycles_per_round)
+{
+    using namespace focr;
+    if (!ctx || !cycles_per_round || wait_kind < 0 || wait_kind > 2 || nwait < 1 || nwait > 8 || iters < 1)
+        return focr_internal_fail(FOCR_ERR_ARG, "focr_bench_pingpong: bad argument");
+    if (cudaSetDevice(focr_internal_device(ctx)) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
+    long long *d = nullptr;
+    if (cudaMalloc((void **)&d, sms * 8) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
+    pingpong_kernel<<<sms, 32 * 9, 0, st>>>(wait_kind, use_commit, nwait, iters, d);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, std::string("pingpong: ") + cudaGetErrorString(e));
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), d, sms * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    std::sort(h.begin(), h.end());
+    *cycles_per_round = (double)h[sms / 2] / iters;
     return FOCR_OK;
 }

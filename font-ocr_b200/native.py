@@ -25,7 +25,7 @@ SYMBOLS = [
     "focr_bank_create", "focr_bank_destroy", "focr_bank_size",
     "focr_ncc_scan", "focr_ncc_scan_device", "focr_process_hits_device", "focr_window_stats", "focr_ncc_numerators",
     "focr_glyph_bank_create", "focr_glyph_bank_destroy", "focr_decode_pages", "focr_sum_of_squares",
-    "focr_host_process_hits", "focr_host_search_c_u8", "focr_bench_umma_i8", "focr_bench_umma_issue_cycles", "focr_bench_tmem",
+    "focr_host_process_hits", "focr_host_search_c_u8", "focr_bench_umma_i8", "focr_bench_umma_issue_cycles", "focr_bench_tmem", "focr_bench_pingpong",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     l.focr_process_hits_device.argtypes = [vp, vp, vp, u32, u32, u32, C.c_float, C.c_int32, u32, u32, vp, vp, vp, vp, vp, vp]
     l.focr_bench_umma_i8.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     l.focr_bench_umma_issue_cycles.restype = C.c_double
+    l.focr_bench_pingpong.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     l.focr_bench_tmem.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     l.focr_host_process_hits.argtypes = [vp, vp, vp, vp, u32, C.c_float, C.c_int32, vp, vp, vp]
     l.focr_host_search_c_u8.argtypes = [vp, u32, u32, vp, u32, u32, C.c_float, vp, vp]

@@ -215,6 +215,9 @@ int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, do
                        double *ms_total);
 
 double focr_bench_umma_issue_cycles(void);
+/* Measurement aid: cycles per hand-shake round trip "signal (tcgen05.commit or arrive) -> nwait warps wait and answer ->
+ * the signaller waits" with the three ways of waiting on an mbarrier (0 try_wait + suspend hint, 1 try_wait, 2 test_wait). */
+int focr_bench_pingpong(focr_ctx *ctx, int wait_kind, int use_commit, int nwait, int iters, double *cycles_per_round);
 
 /* Measurement aid: TMEM <-> register traffic (tcgen05.ld / tcgen05.st 32x32b.x32) from nw warps, optionally
  * while another warp streams MMAs of N = mma_n; mode 0 = ld, 1 = ld + st, 2 = st, 3 = ld + the screen's max tree.
