@@ -312,6 +312,35 @@ def run_ours(args):
         except Exception as ex:  # never let the extra measurement break the bench line
             post = {"error": str(ex)[:200]}
 
+    # BASELINE config 4 beside the headline: focr's least-squared-distance line decode (main.rs:87-218,
+    # -x 45 -y 39 -w 608 --line-height 12 --line-advance 15) on 2480x3508 pages through the host-buffer C ABI
+    # (H2D of the pages and D2H of the glyph indices inside the timed region), with the cached glyph rasters
+    focr_line = None
+    if rank == 0 and not args.no_focr:
+        try:
+            from font_ocr_b200 import focr
+            fbank = focr.GlyphBank(ctx, font, TEXT_SIZE)
+            fdistinct = [pkg.pages.make_focr_page(font, TEXT_SIZE, R_W, R_H, seed=7000 + i)[0] for i in range(4)]
+            fpages = np.stack([fdistinct[i % 4] for i in range(32)])
+            fP, fmax = len(fpages), (R_H - 39 + 14) // 15
+            fg = np.zeros((fP, fmax, 512), np.uint16)
+            fn_, fy, fl = np.zeros((fP, fmax), np.uint32), np.zeros((fP, fmax), np.uint32), np.zeros(fP, np.uint32)
+            ts = []
+            for _ in range(4):  # first call = warm-up
+                t0 = time.perf_counter()
+                native.check(native.lib().focr_decode_pages(ctx._h, fbank._h, native.ptr(fpages), R_W * R_H, R_W, R_H, fP, 45, 39, 608,
+                                                            12, 15, fmax, 512, native.ptr(fg), native.ptr(fn_), native.ptr(fy),
+                                                            native.ptr(fl)))
+                ts.append(time.perf_counter() - t0)
+            dt = float(np.median(ts[1:]))
+            focr_line = {"workload": "config4: focr line decode, 32 pages 2480x3508, -x 45 -y 39 -w 608 --line-height 12 --line-advance 15, "
+                                     "67 glyphs x 64 phases cached",
+                         "pages_per_s": fP / dt, "lines_per_page": float(fl.mean()), "cells_per_s": float(fn_.sum()) / dt,
+                         "timing": "host wall clock around focr_decode_pages (pageable host pages -> H2D -> kernel -> D2H of the glyph indices), median of 3"}
+            fbank.close()
+        except Exception as ex:
+            focr_line = {"error": str(ex)[:200]}
+
     total_pages = P * world
     value = total_pages * args.steps / (ms_dev / 1e3)
     e2e_value = total_pages * args.steps / (ms_e2e / 1e3)
@@ -387,7 +416,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(out_pin.numel() + counts_pin.numel() * 4) * world,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "process_hits_device": post,
+            "process_hits_device": post, "focr": focr_line,
         }
     bank.close()
     ctx.close()
@@ -410,6 +439,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-stride", type=int, default=8, help="CPU baseline scans every k-th template")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-focr", action="store_true", help="skip the config-4 focr line-decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
