@@ -246,3 +246,70 @@ def test_process_hits_on_device(ctx, oracle, font, pkg):
         assert got[P - 1] == []
     assert any(len(lines) > 0 for lines in got)
     bank.close()
+
+
+def test_scan_edge_cases_vs_oracle(kctx, oracle):
+    """Edge cases of the screen + exact pass design, each against the oracle: more templates of one size than one
+    launch holds (several launches, column remapping), thresholds that make every window a hit (candidate-list
+    overflow and retry, the 1024/n_out cut), saturated pages where b*S + a*P leaves the linear range of the fp32
+    trick ("always a candidate" windows), constant pages, n_out = 1, a page smaller than the template."""
+    rng = np.random.default_rng(77)
+
+    def check(page, tpls, thr, n_out, tag):
+        m, c = _scan(kctx, tpls, page, thr, n_out)
+        s = oracle.Searcher(page, "port")
+        exp = [s.search_c_u8(t, thr, n_out=n_out, allow_wide=True) for t in tpls]
+        _assert_same(m[0], c[0], exp, tag)
+        return c
+
+    # 600 templates of one box size: three launches of the tcgen05 kernel
+    page = rng.integers(0, 256, (70, 180), dtype=np.uint8)
+    page[rng.random(page.shape) < 0.7] = 255
+    tpls = [rng.integers(0, 256, (9, 11), dtype=np.uint8) for _ in range(600)]
+    check(page, tpls, 0.25, 1024, "600 templates")
+
+    # every window is a hit: thr < -1
+    page = rng.integers(0, 256, (120, 260), dtype=np.uint8)
+    tpls = [rng.integers(0, 256, (9, 9), dtype=np.uint8) for _ in range(40)]
+    c = check(page, tpls, -1.5, 64, "thr -1.5")
+    assert (c == 64).all()
+    c = check(page, tpls, -0.2, 1024, "thr -0.2")
+    assert c.max() == 1024
+
+    # saturated (nearly black) page and bright 16x16 templates: s_p and b = s_n/n are both near their maxima
+    page = rng.integers(0, 12, (90, 200), dtype=np.uint8)
+    page[30:50, 40:90] = rng.integers(0, 256, (20, 50), dtype=np.uint8)
+    tpls = [np.clip(rng.integers(200, 256, (16, 16)) - (rng.random((16, 16)) < 0.1) * 150, 0, 255).astype(np.uint8) for _ in range(12)]
+    check(page, tpls, 0.05, 1024, "saturated")
+
+    # constant pages: every window is constant -> rnorm_p = inf -> no hit
+    for v in (0, 255, 131):
+        c = check(np.full((64, 100), v, np.uint8), tpls[:3], 0.1, 1024, f"constant {v}")
+        assert c.sum() == 0
+
+    # n_out = 1 and a page that is smaller than the template in one direction (no window at all)
+    page = rng.integers(0, 256, (40, 60), dtype=np.uint8)
+    tpls = [rng.integers(0, 256, (7, 8), dtype=np.uint8) for _ in range(5)]
+    check(page, tpls, 0.0, 1, "n_out 1")
+    m, c = _scan(kctx, [rng.integers(0, 256, (12, 20), dtype=np.uint8)], rng.integers(0, 256, (10, 64), dtype=np.uint8), 0.1)
+    assert c.sum() == 0
+
+
+def test_sub_block_launch_matches_oracle(ctx, oracle, monkeypatch):
+    """FOCR_TC_SPLIT=1: a launch covers its columns as two accumulator-sized sub-blocks per row (two jobs per row that
+    share the row's operands).  Same results as the oracle."""
+    from font_ocr_b200 import native
+
+    monkeypatch.setenv("FOCR_TC_SPLIT", "1")
+    ctx.set_kernel(native.KERNEL_TCGEN05)
+    try:
+        rng = np.random.default_rng(5)
+        page = rng.integers(0, 256, (150, 300), dtype=np.uint8)
+        page[rng.random(page.shape) < 0.75] = 255
+        tpls = [rng.integers(0, 256, (14, 15), dtype=np.uint8) for _ in range(200)]
+        m, c = _scan(ctx, tpls, page, 0.2)
+        s = oracle.Searcher(page, "port")
+        _assert_same(m[0], c[0], [s.search_c_u8(t, 0.2) for t in tpls], "split")
+        assert c.sum() > 0
+    finally:
+        ctx.set_kernel(native.KERNEL_AUTO)
