@@ -62,9 +62,9 @@ constexpr int TC_G = 4;               // rows per pipeline group: one mbarrier h
 constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
 constexpr int TC_RAW_SLOTS = TC_RAW_GROUPS * TC_G;
 constexpr int TC_RAW_BYTES = 160;
-constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side may run ahead of the MMA
+constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side may run ahead of the MMA (1 for tall boxes)
 constexpr int TC_RING_MAX = 12;       // max ring groups
-constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: 4 groups x 4 output rows x 2 KB
+constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: up to 4 groups x 4 output rows x 2 KB (2 for tall boxes)
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
 constexpr int TC_YSEG = 128;          // output rows per work item
 // setmaxnreg budget (the kernel is compiled for 72 registers x 896 threads): warps 0-3 (TMA producer, MMA issuer) keep
@@ -81,7 +81,7 @@ constexpr int TC_REGS_TOEPLITZ = 40;
 constexpr int TC_REGS_A2 = 48;
 constexpr int TC_REGS_EPILOGUE = 88;
 constexpr int TC_REGS_ISSUE = 64;
-constexpr size_t TC_SMEM_BUDGET = 200 * 1024;
+constexpr size_t TC_SMEM_BUDGET = 220 * 1024;
 constexpr float TC_C0 = 16711680.f;               // 2^15 * 510 = 2^24 - 2^16: the constant term of the fp16 MMA
 constexpr float TC_KCAP = 8323072.f - 8192.f;     // C0 - 2^23 minus slack: largest b*S + a*P that keeps F in [2^23, 2^24)
 constexpr float TC_BIG = 60000.f;                 // fp16-representable "never" marker (BIG*BIG = 3.6e9 >> any acc)
@@ -102,6 +102,9 @@ struct TcParams {
     int nbpp;          // accumulators per pipeline (issuing thread + epilogue team) = nbuf / 2
     int ring;          // expanded-row ring slots = ring_groups * 4
     int ring_groups;
+    int n_mirror;      // ring slots stored twice (see tc_mma_role); 0: the issue loop wraps every K step (np == 32)
+    int a2_groups;     // groups of the A2 ring (<= TC_A2_GROUPS)
+    int sshift;        // the templates of the B tile are ceil(t / 2^sshift): S is split at bit 10 instead of 6 (see A2 rows)
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
     const uint8_t *btile;     // [nsub][2*ksteps][nbs][16]
@@ -420,10 +423,12 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const uint32_t a_lo0 = ((smem_u32(sm.ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
     const uint32_t b_lo0 = ((smem_u32(sm.btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
     const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
-    const uint32_t a2_addr16 = (smem_u32(sm.a2ring) & 0x3FFFFu) >> 4, a2_wrap16 = TC_A2_GROUPS * TC_G * (2048u >> 4);
+    const uint32_t a2_addr16 = (smem_u32(sm.a2ring) & 0x3FFFFu) >> 4, a2_wrap16 = (uint32_t)p.a2_groups * TC_G * (2048u >> 4);
     const uint32_t a2_end16 = a2_addr16 + a2_wrap16;
     const uint32_t b2_lo = ((smem_u32(sm.b2tile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
     const bool corr = p.dbg_acc == nullptr;
+    const uint32_t a2_groups = p.a2_groups;
+    const bool wrap = p.n_mirror == 0;       // no mirror slots: a row's K steps may run past the end of the ring
     const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : 1u;
     uint64_t *const a_full = sm.a_full, *const a_empty = sm.a_empty, *const a2_full = sm.a2_full, *const a2_empty = sm.a2_empty,
                     *const t_full = sm.t_full, *const t_empty = sm.t_empty;
@@ -460,7 +465,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
             while (corr && rows2_ready <= o) {
                 TT(1, mbar_wait(a2_full + new2_g, new2_par, p.wd, 14 + mw, o, sm.prog));
                 rows2_ready += TC_G;
-                if (++new2_g == TC_A2_GROUPS) new2_g = 0, new2_par ^= 1;
+                if (++new2_g == a2_groups) new2_g = 0, new2_par ^= 1;
             }
             // one job per sub-block: the row's operands are shared, the templates (B, B2) and the accumulator differ
             uint32_t b_lo = b_lo0, b2 = b2_lo;
@@ -480,9 +485,12 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
                         tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo + k * b_inc), idesc8,
                                      (corr || k) ? 1u : 0u);
                 } else {
-                    for (uint32_t k = 0; k < ksteps; k++)
-                        tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo + k * b_inc), idesc8,
-                                     (corr || k) ? 1u : 0u);
+                    uint32_t al = a_first;
+                    for (uint32_t k = 0; k < ksteps; k++) {
+                        tc_mma_i8_if(mma_on, d0, desc_hi | al, desc_hi | (b_lo + k * b_inc), idesc8, (corr || k) ? 1u : 0u);
+                        al += a_inc;
+                        if (wrap && al >= a_end) al -= a_wrap;
+                    }
                 }
                 if (tron) tacc[3] += clock64() - ti_;
                 TT(4, tc_commit(t_full + acc));   // accumulator ready for the epilogue
@@ -505,7 +513,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
             while (rel2_rows <= o_next) {
                 TT(4, tc_commit(a2_empty + rel2_g));
                 rel2_rows += TC_G;
-                if (++rel2_g == TC_A2_GROUPS) rel2_g = 0;
+                if (++rel2_g == a2_groups) rel2_g = 0;
             }
         }
         // next item: its first row follows this item's last page row
@@ -525,9 +533,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     // ---- shared memory carve-up (all blocks multiples of 128 B)
     uint8_t *btile = smem;
     uint8_t *ring = btile + ((p.btile_bytes + 127) & ~127u);
-    uint8_t *raw = ring + (size_t)(p.ring + p.n_hp) * p.row_pitch;  // + mirror slots: slot ring+i repeats slot i (i < n_hp-1)
+    uint8_t *raw = ring + (size_t)(p.ring + p.n_mirror) * p.row_pitch;  // + mirror slots: slot ring+i repeats slot i
     uint8_t *a2ring = raw + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127);  // [TC_A2_GROUPS*4][128][16 B] fp16 x 8
-    uint8_t *b2tile = a2ring + TC_A2_GROUPS * TC_G * 2048;                // [2][nb][16 B]: chunk 0 constants, chunk 1 zeros
+    uint8_t *b2tile = a2ring + (size_t)p.a2_groups * TC_G * 2048;         // [nsub][2][nbs][16 B]: chunk 0 constants, chunk 1 zeros
     uint64_t *bars = (uint64_t *)(b2tile + (size_t)2 * p.nb * 16);   // b2tile: [nsub][2][nbs][16]
     uint64_t *bar_btile = bars;                       // 1
     uint64_t *raw_full = bars + 1;                    // TC_RAW_GROUPS
@@ -574,7 +582,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const __half a1 = __float2half_rn(a), b1 = __float2half_rn(b);
         const __half a2 = __float2half_rn(a - __half2float(a1)), b2 = __float2half_rn(b - __half2float(b1));
         const __half big = __float2half_rn(-TC_BIG), padh = __float2half_rn(pad ? -TC_BIG : 510.f);
-        __align__(16) __half h[8] = {__hneg(b1), __hneg(b2), __hneg(b1), __hneg(a1), __hneg(a2), __hneg(a1), big, padh};
+        // sshift > 0: the A2 rows carry S_hi/16 (S may exceed the fp16 range), so the factors of S_hi carry the 16
+        const __half b1h = p.sshift ? __float2half_rn(16.f * __half2float(b1)) : b1;
+        const __half b2h = p.sshift ? __float2half_rn(16.f * __half2float(b2)) : b2;
+        __align__(16) __half h[8] = {__hneg(b1h), __hneg(b2h), __hneg(b1), __hneg(a1), __hneg(a2), __hneg(a1), big, padh};
         const int sb = t / p.nbs, n = t - sb * p.nbs;      // layout [sub][K chunk][column][16 B]
         uint8_t *dst = b2tile + ((size_t)sb * 2 * p.nbs + n) * 16;
         *(uint4 *)dst = *(const uint4 *)h;
@@ -646,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         if (elect_one()) {
             TcSmem sm = {btile, ring, a2ring, b2tile, bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty, prog};
             const uint32_t mw = warp - 1;
-            switch (p.ksteps) {
+            switch (p.n_mirror ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
                 case 6: tc_mma_role<6>(p, sm, mw); break;
                 case 7: tc_mma_role<7>(p, sm, mw); break;
                 case 8: tc_mma_role<8>(p, sm, mw); break;
@@ -660,7 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         // ================================================================== Toeplitz expansion
         // one warp per page row, four rows (one group) in flight per handshake
         const int w = warp - 4;
-        const uint32_t n_mirror = p.n_hp - 1;   // slots 0 .. n_hp-2 are stored twice, so an output row never wraps
+        const uint32_t n_mirror = p.n_mirror;   // slots 0 .. n_mirror-1 are stored twice, so an output row never wraps
         const uint32_t ring_g = p.ring_groups;
         uint32_t rg = 0, rgpar = 0, ag = 0, agpar = 1;
         bool first_round = true;
@@ -747,7 +758,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     const bool lin = valid && (p.bmax * (float)sv[i] + p.amax * pv[i] <= TC_KCAP);
                     const uint32_t s = lin ? sv[i] : 0u;
                     const float P = lin ? pv[i] : 0.f;
-                    const float s_hi = (float)(s & ~63u), s_lo = (float)(s & 63u);
+                    // S = S_hi + S_lo, both exact in fp16: split at bit 6 (S < 2^16), or at bit 10 with S_hi stored /16 for
+                    // boxes of more than 256 pixels (S < 2^19); the factor 16 is in B2
+                    const float s_hi = p.sshift ? (float)((s & ~1023u) >> 4) : (float)(s & ~63u);
+                    const float s_lo = p.sshift ? (float)(s & 1023u) : (float)(s & 63u);
                     const __half p1 = __float2half_rn(P);
                     const __half p2 = __float2half_rn(P - __half2float(p1));
                     const __half shi = __float2half_rn(s_hi), slo = __float2half_rn(s_lo);
@@ -759,7 +773,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(a2_full + ag);
-            if (++ag == TC_A2_GROUPS) ag = 0, agpar ^= 1, first_round = false;
+            if (++ag == (uint32_t)p.a2_groups) ag = 0, agpar ^= 1, first_round = false;
         }
         if (w == 0 && lane == 0) TT_END(24);
     } else {
@@ -973,10 +987,10 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_hp, int row_pitch, int nb)
+static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_mirror, int row_pitch, int nb, int a2_groups)
 {
-    return ((btile_bytes + 127) & ~127u) + (size_t)(ring + n_hp) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
-           (size_t)TC_A2_GROUPS * TC_G * 2048 + (size_t)2 * nb * 16 +
+    return ((btile_bytes + 127) & ~127u) + (size_t)(ring + n_mirror) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
+           (size_t)a2_groups * TC_G * 2048 + (size_t)2 * nb * 16 +
            (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 2 * TC_MAX_BUF) * 8 + 64 + 128;
 }
 
@@ -991,15 +1005,27 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     const uint32_t n_hp = np == 16 ? (n_h + 1) & ~1u : n_h;
     tc.kchunks = n_h * (np / 16);
     tc.ksteps = (tc.kchunks + 1) / 2;
-    const int ring_groups = ((int)n_hp + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;
-    const int ring = ring_groups * TC_G;
+    // tall boxes: less look-ahead and a shorter A2 ring leave room for the B tile; boxes wider than 16 (np == 32) take
+    // one ring slot per K step, so the issue loop can wrap and the mirror slots are not needed
+    const bool tall = n_hp > 16;
+    tc.look_groups = tall ? 1 : TC_LOOK_GROUPS;
+    tc.a2_groups = tall ? 2 : TC_A2_GROUPS;
+    tc.n_mirror = np == 16 ? n_hp - 1 : 0;
+    tc.ring_groups = (n_hp + TC_G - 1 + TC_G - 1) / TC_G + tc.look_groups;
+    const int ring = tc.ring_groups * TC_G;
     const int row_pitch = np == 16 ? 2048 : 2304;
-    if (ring_groups > TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
-    // the fp16 statistics operand needs s_p <= 255*n <= 65504 (fp16 range); larger boxes take the SIMT kernel
-    if (n_w * n_h > 256) return 0;
+    if (tc.ring_groups > (uint32_t)TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
+    // Boxes of more than 256 pixels: b*S + a*P outgrows the 23-bit linear range of the fp32 trick, so the SCREEN runs at
+    // 1/2^sshift scale: the B tile holds ceil(t / 2^sshift) (acc' >= acc / 2^sshift: still errs towards more
+    // candidates), b and a are divided by 2^sshift; the exact pass uses the true templates.
+    tc.sshift = 0;
+    while ((n_w * n_h) > (256u << tc.sshift)) tc.sshift++;
+    if (tc.sshift > 3) return 0;
     // largest column count per launch (multiple of 32, <= 256) whose B tiles fit next to the rings
     int nb_max = 256;
-    while (nb_max >= 32 && tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)n_hp, row_pitch, nb_max) > TC_SMEM_BUDGET) nb_max -= 32;
+    while (nb_max >= 32 &&
+           tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)tc.n_mirror, row_pitch, nb_max, (int)tc.a2_groups) > TC_SMEM_BUDGET)
+        nb_max -= 32;
     if (nb_max < 32) return 0;
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
     const uint32_t per_blk = (n_tpl + tc.n_blocks - 1) / tc.n_blocks;   // templates per launch
@@ -1027,18 +1053,21 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
         const uint32_t col = sub * tc.nbsub + n;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
             const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
-            memcpy(&bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16], rows_host + ((size_t)i * n_h + row) * np + boff, 16);
+            uint8_t *dst = &bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16];
+            const uint8_t *src = rows_host + ((size_t)i * n_h + row) * np + boff;
+            for (int q = 0; q < 16; q++) dst[q] = (uint8_t)((src[q] + (1u << tc.sshift) - 1u) >> tc.sshift);
         }
         const TplInfo &ti = info[i];
         // norm_n = sqrt(s2_n - s_n^2/n) = 1/rnorm_n ; constant (incl. all-zero) templates can never hit
-        const double norm_n = 1.0 / ti.rnorm_n;
+        const double scale = 1.0 / (double)(1u << tc.sshift);
+        const double norm_n = scale / ti.rnorm_n, b_t = scale * ti.s_n * ti.n_recip;
         const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
-        cst[(size_t)blk * tc.nb + col] = make_float2(ok ? (float)norm_n : inf, (float)(ti.s_n * ti.n_recip));
+        cst[(size_t)blk * tc.nb + col] = make_float2(ok ? (float)norm_n : inf, (float)b_t);
         tof[(size_t)blk * tc.nb + col] = bank_index[i];
         cof[(size_t)blk * tc.nb + col] = i;
         tc.col_of[i] = blk * tc.nb + col;
         if (ok) {
-            tc.blk_bmax[blk] = std::max(tc.blk_bmax[blk], (float)(ti.s_n * ti.n_recip));
+            tc.blk_bmax[blk] = std::max(tc.blk_bmax[blk], (float)b_t);
             tc.blk_normmax[blk] = std::max(tc.blk_normmax[blk], (float)norm_n);
         }
     }
@@ -1074,6 +1103,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
                            cudaStream_t st, int *n_launches, uint32_t *dbg_acc, int dbg_pos, TcHook *hook)
 {
     if (!tc.supported) return cudaErrorNotSupported;
+    if (dbg_acc && tc.sshift) return cudaErrorNotSupported;  // the screen of a > 256-pixel box runs on scaled templates: no raw numerators
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.inv = a.inv;
@@ -1095,7 +1125,10 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     // count the owners alternate, a waiter can fall two phases behind and the parity test aliases.)
     p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF) & ~1;
     p.nbpp = p.nbuf / 2;
-    p.ring_groups = (p.n_hp + TC_G - 1 + TC_G - 1) / TC_G + TC_LOOK_GROUPS;  // rows y..y+n_hp-1 may straddle one more group
+    p.ring_groups = tc.ring_groups;   // rows y..y+n_hp-1 may straddle one more group; + look-ahead
+    p.n_mirror = tc.n_mirror;
+    p.a2_groups = tc.a2_groups;
+    p.sshift = tc.sshift;
     p.ring = p.ring_groups * TC_G;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
     p.n_entries = tc.np == 16 ? 128 : 144;
@@ -1116,7 +1149,7 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     if (xs <= 0 || ys <= 0) return cudaSuccess;
     p.n_xstrips = (xs + 127) / 128;
     p.n_ysegs = (ys + TC_YSEG - 1) / TC_YSEG;
-    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_hp, p.row_pitch, p.nb);
+    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_mirror, p.row_pitch, p.nb, p.a2_groups);
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int items = n_pages * p.n_xstrips * p.n_ysegs;

@@ -18,6 +18,9 @@ struct TcClass {
     uint32_t nsub = 0;      // sub-blocks per launch: every output row is nsub jobs (one accumulator each) sharing its operands
     uint32_t nbsub = 0;     // columns per sub-block = N of the MMAs (multiple of 32, <= 128 when nsub > 1)
     uint32_t n_blocks = 0;  // launches per chunk of pages
+    uint32_t sshift = 0;    // boxes with more than 256 pixels: the screen runs on templates scaled by 2^-sshift (rounded up)
+    uint32_t n_mirror = 0;  // ring slots stored twice (np == 16: an output row never wraps); 0 = the issue loop wraps
+    uint32_t look_groups = 0, a2_groups = 0, ring_groups = 0;  // ring sizing of this class
     uint32_t kchunks = 0;   // 16-byte K chunks per template = n_h * np/16
     uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
     uint8_t *b_tiles = nullptr;   // device [n_blocks][2*ksteps][nb][16]

@@ -313,3 +313,26 @@ def test_sub_block_launch_matches_oracle(ctx, oracle, monkeypatch):
         assert c.sum() > 0
     finally:
         ctx.set_kernel(native.KERNEL_AUTO)
+
+
+def test_large_box_bank_on_the_tensor_core(ctx, oracle, font, pkg):
+    """BASELINE config 5 shape (-t 24, box about 27x26 > 256 pixels, wider than the AVX2 kernel's 16): the tcgen05
+    kernel screens with templates scaled by 2^-sshift and the exact pass restores the reference arithmetic; the oracle
+    here is the C restatement with the width limit lifted (the compiled reference panics for n_w > 16, ncc.rs:392)."""
+    from font_ocr_b200 import native
+
+    bank = pkg.raster.TemplateBank(font, 24, x_bits=1)
+    tpls = [t.pixels for t in bank.templates]
+    assert max(t.shape[0] * t.shape[1] for t in tpls) > 256 and max(t.shape[1] for t in tpls) > 16
+    page, lines, _ = pkg.pages.make_ncc_page(bank, 900, 260, seed=2, shifts="bank")
+    ctx.set_kernel(native.KERNEL_TCGEN05)
+    try:
+        m, c = _scan(ctx, tpls, page, 0.8)
+    finally:
+        ctx.set_kernel(native.KERNEL_AUTO)
+    s = oracle.Searcher(page, "port")
+    sample = list(range(0, len(tpls), 7))
+    for t in sample:
+        exp = s.search_c_u8(tpls[t], 0.8, allow_wide=True)
+        _assert_same(m[0, t:t + 1], c[0, t:t + 1], [exp], f"template {t}")
+    assert c.sum() > len(lines)
