@@ -825,12 +825,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
                 }
                 tc_fence_after();
+                const long long tseen_ = tron ? clock64() : 0;
                 const uint32_t tb = tlane + acc * p.nbs;
                 const uint32_t cbase = p.col_base + sb * p.nbs;
                 auto release = [&]() {  // every tcgen05.ld of this job has completed: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + acc);
+                    if (tron) tacc[3] += clock64() - tseen_;   // time from "accumulator full" seen to "accumulator released"
                 };
                 auto screen = [&](uint32_t (&v)[32], int u) {
                     float t[11];
@@ -887,6 +889,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                         if (h3) screen(vb, u3);
                     }
                 }
+                if (tron) tacc[4] += clock64() - tseen_;       // ... to the end of the job (screens, candidates)
                 if (++kb == nbpp) kb = 0, kpar ^= 1;
               }
               if (TC_TEAMS == 1 && pipe) {
