@@ -95,7 +95,6 @@ struct focr_ctx {
     uint32_t hits_per_page = 2u << 20;
     uint32_t cand_per_warp = 16384;  // capacity of each epilogue warp's private candidate list (grows on overflow)
     int sm_count = 148;
-    TcWorkspace tc;
     // per-stage profiling (focr_ctx_profile)
     bool profile = false;
     struct Span { cudaEvent_t a, b; int stage; int launches; };
@@ -191,7 +190,6 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
         if (s.ev_compute) cudaEventDestroy(s.ev_compute);
         if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
-    tc_workspace_release(c->tc);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->h2d);
     cudaStreamDestroy(c->d2h);
@@ -479,7 +477,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
             StageTimer tm(c, FOCR_STAGE_SCAN);
             if (tc) {
                 ExactStage hook(c);
-                CU(launch_scan_tc(c->tc, ch.tc, a, nB, c->sm_count, st, &nl, nullptr, -1, &hook));
+                CU(launch_scan_tc(ch.tc, a, nB, c->sm_count, st, &nl, nullptr, -1, &hook));
             }
             else
                 CU(launch_scan_simt(a, nB, st, &nl));
@@ -809,7 +807,7 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
         a.cls.tpl_index = ch.index_dev.as<uint32_t>();
         a.cls.rows = ch.rows.as<uint8_t>();
         a.acc_out = nullptr;
-        CU(launch_scan_tc(c->tc, ch.tc, a, 1, c->sm_count, st, &nl, s.acc.as<uint32_t>(), (int)pos));
+        CU(launch_scan_tc(ch.tc, a, 1, c->sm_count, st, &nl, s.acc.as<uint32_t>(), (int)pos));
     } else {
         CU(launch_scan_simt(a, 1, st, &nl));
     }

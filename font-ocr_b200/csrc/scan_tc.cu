@@ -124,7 +124,6 @@ struct TcParams {
     unsigned int *wd;   // watchdog words (see mbar_wait): [0] raised, [1] tag, [2] info, [3] CTA, [4] warp, [5] parity
     long long *trace;   // timing experiments (env FOCR_TC_TRACE=file): CTA 0's roles add up the cycles they spend in each
                         // wait / phase, [64] (tools/tc_trace.py names the slots)
-    int spin;           // bit 0: epilogue polls t_full, bit 1: MMA warps poll t_empty (env FOCR_TC_SPIN, default 3)
     int dbg_mode;       // timing experiments only (env FOCR_TC_DBG, a bit mask; results are wrong when non-zero):
                         // 1 epilogue skips the TMEM reads, 2 epilogue loads but does not screen, 4 no MMAs are issued,
                         // 8 A2 rows skip their global loads, 16 no Toeplitz expansion, 32 A2 rows skip their stores
@@ -214,22 +213,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsign
             }
         }
     }
-}
-// Latency-critical waits (accumulator hand-offs): plain polling, no suspend -- the wake-up of a parked thread
-// costs more than the whole epilogue of a row.
-__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity)
-{
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -1100,9 +1083,8 @@ void tc_class_release(TcClass &tc)
 }
 
 bool tc_class_supported(const TcClass &tc) { return tc.supported; }
-void tc_workspace_release(TcWorkspace &) {}
 
-cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
+cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
                            cudaStream_t st, int *n_launches, uint32_t *dbg_acc, int dbg_pos, TcHook *hook)
 {
     if (!tc.supported) return cudaErrorNotSupported;
@@ -1163,8 +1145,6 @@ cudaError_t launch_scan_tc(TcWorkspace &, const TcClass &tc, const ScanArgs &a, 
     {
         const char *dm = getenv("FOCR_TC_DBG");
         p.dbg_mode = dm ? atoi(dm) : 0;
-        const char *sp = getenv("FOCR_TC_SPIN");
-        p.spin = sp ? atoi(sp) : 3;
     }
     uint4 *wdlog = nullptr;
     if (getenv("FOCR_TC_WDLOG") && cudaMalloc((void **)&wdlog, (size_t)grid * 32 * sizeof(uint4)) == cudaSuccess) {

@@ -31,10 +31,6 @@ struct TcClass {
     std::vector<float> blk_bmax, blk_normmax;  // host, per N-block: max s_n/n and max norm_n over its real columns
 };
 
-struct TcWorkspace {
-    void *work_counter = nullptr;  // device: dynamic tile scheduler counter
-};
-
 // optional instrumentation around the exact pass (api.cu times it as its own stage)
 struct TcHook {
     virtual void exact_begin() {}
@@ -46,9 +42,8 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
                    const uint32_t *bank_index, const TplInfo *info);
 void tc_class_release(TcClass &tc);
 bool tc_class_supported(const TcClass &tc);
-void tc_workspace_release(TcWorkspace &ws);
 // dbg_acc/dbg_pos: parity probe -- store the raw numerators of the class's dbg_pos-th template
-cudaError_t launch_scan_tc(TcWorkspace &ws, const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
+cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, int sm_count,
                            cudaStream_t st, int *n_launches, uint32_t *dbg_acc = nullptr, int dbg_pos = -1,
                            TcHook *hook = nullptr);
 

@@ -6,12 +6,12 @@ import torch
 import bench
 from font_ocr_b200 import native, ncc
 
-modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1, 5, 7, 8]
+modes = [int(m) for m in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1, 2, 4, 61]  # bit mask, see scan_tc.cu (experiments build)
 P = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 pkg, font, bank_h = bench.make_bank()
 tpls = [t.pixels for t in bank_h.templates]
-if len(sys.argv) > 4:  # only the templates of one box width
-    tpls = [t for t in tpls if t.shape[1] == int(sys.argv[4])]
+if len(sys.argv) > 3:  # only the templates of one box width
+    tpls = [t for t in tpls if t.shape[1] == int(sys.argv[3])]
 T = len(tpls)
 print("templates", T, "box", tpls[0].shape)
 ctx = ncc.Context(0)
@@ -19,10 +19,8 @@ bank = ncc.Bank(ctx, tpls)
 pages = torch.from_numpy(bench.make_pages(pkg, bank_h, P, 0, distinct=8)).cuda()
 out = torch.empty(P * T * 1024 * 8, dtype=torch.uint8, device="cuda")
 cnt = torch.empty(P * T, dtype=torch.int32, device="cuda")
-spins = [int(m) for m in sys.argv[3].split(",")] if len(sys.argv) > 3 else [3]
-for mode, spin in [(m, sp) for sp in spins for m in modes]:
+for mode in modes:
     os.environ["FOCR_TC_DBG"] = str(mode)
-    os.environ["FOCR_TC_SPIN"] = str(spin)
     for i in range(3):
         if i == 2:
             ctx.profile(True); ctx.profile_read()
@@ -30,4 +28,4 @@ for mode, spin in [(m, sp) for sp in spins for m in modes]:
                               out.data_ptr(), cnt.data_ptr())
     pr = ctx.profile_read(); ctx.profile(False)
     tot = sum(v[0] for k, v in pr.items() if k != "exact")
-    print("spin", spin, "mode", mode, "pages/s %.1f" % (P / tot * 1e3), {k: round(v[0] / P, 4) for k, v in pr.items()}, "ms/page", flush=True)
+    print("mode", mode, "pages/s %.1f" % (P / tot * 1e3), {k: round(v[0] / P, 4) for k, v in pr.items()}, "ms/page", flush=True)
