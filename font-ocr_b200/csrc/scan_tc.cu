@@ -168,6 +168,33 @@ __device__ uint32_t g_wdprog[32];
 // Watchdog: a wait that has timed out ~8000 times (>= 0.15 s) records who is stuck (wd[1..4] = tag, info, CTA,
 // warp) and raises wd[0]; every waiting thread that sees wd[0] gives up, so a protocol bug ends the kernel with an
 // error the host reports instead of hanging the GPU.
+// slow path of the watchdog, OUT OF LINE: the wait loops sit in single-warp roles whose speed depends on how few
+// instructions and instruction-cache lines they touch (inlining this at every wait cost 12 % of the kernel's speed).
+// Returns true when the wait must give up.
+__device__ __noinline__ bool mbar_watchdog(unsigned int *wd, uint32_t tries, uint32_t tag, uint32_t info, uint32_t parity,
+                                           uint32_t addr, volatile uint32_t *prog)
+{
+    if (tries == 4096u && prog && atomicCAS(wd + 6, 0u, 1u) == 0u) {  // first long wait anywhere: snapshot of the CTA's progress
+        for (int i = 0; i < 32; i++) g_wdprog[i] = prog[i];
+        wd[7] = blockIdx.x, wd[8] = threadIdx.x >> 5, wd[9] = tag;
+        __threadfence();
+    }
+    if (tries == 8192u && g_wdlog) {  // debugging aid (env FOCR_TC_WDLOG): what this warp has been stuck on
+        uint4 *slot = g_wdlog + (size_t)blockIdx.x * 32 + (threadIdx.x >> 5);
+        if (slot->x == 0) *slot = make_uint4(tag, info, parity, addr);
+    }
+    // give up after ~0.3 s, or ~0.15 s when another wait has already given up
+    if (tries >= 16384u || (tries >= 8192u && *(volatile unsigned int *)wd != 0)) {
+        if (atomicCAS(wd, 0u, 1u) == 0u) {
+            wd[1] = tag, wd[2] = info, wd[3] = blockIdx.x, wd[4] = threadIdx.x >> 5;
+            wd[5] = parity;
+            __threadfence();
+        }
+        return true;
+    }
+    return false;
+}
+
 template <bool HINT = true>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
                                           uint32_t info = 0, volatile uint32_t *prog = nullptr)
@@ -192,26 +219,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsign
                 : "r"(addr), "r"(parity)
                 : "memory");
         if (done) return;
-        if (wd && (++tries & 63u) == 0) {
-            if (tries == 4096u && prog && atomicCAS(wd + 6, 0u, 1u) == 0u) {  // first long wait anywhere: snapshot of the CTA's progress
-                for (int i = 0; i < 32; i++) g_wdprog[i] = prog[i];
-                wd[7] = blockIdx.x, wd[8] = threadIdx.x >> 5, wd[9] = tag;
-                __threadfence();
-            }
-            if (tries == 8192u && g_wdlog) {  // debugging aid (env FOCR_TC_WDLOG): what this warp has been stuck on
-                uint4 *slot = g_wdlog + (size_t)blockIdx.x * 32 + (threadIdx.x >> 5);
-                if (slot->x == 0) *slot = make_uint4(tag, info, parity, addr);
-            }
-            // give up after ~0.3 s, or ~0.15 s when another wait has already given up
-            if (tries >= 16384u || (tries >= 8192u && *(volatile unsigned int *)wd != 0)) {
-                if (atomicCAS(wd, 0u, 1u) == 0u) {
-                    wd[1] = tag, wd[2] = info, wd[3] = blockIdx.x, wd[4] = threadIdx.x >> 5;
-                    wd[5] = parity;
-                    __threadfence();
-                }
-                return;
-            }
-        }
+        if (wd && (++tries & 63u) == 0 && mbar_watchdog(wd, tries, tag, info, parity, addr, prog)) return;
     }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
@@ -384,7 +392,9 @@ struct TcSmem {
 // KS = K steps per output row as a compile-time constant (0: generic loop): the issue sequence is straight-line
 // code, and because the ring stores its first n_hp-1 slots twice, every descriptor of a row is the first one plus
 // a constant.
-template <int KS>
+// LEAN = the common case (one sub-block per row, no parity probe): the per-row instruction stream of this thread sets the
+// speed of the kernel (every ~10 instructions per row cost 1-2 %), so that case is compiled without the extras.
+template <int KS, bool LEAN>
 __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t mw)
 {
     const uint32_t idesc8 = (2u << 4)                          // D format: S32
@@ -409,7 +419,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const uint32_t a2_addr16 = (smem_u32(sm.a2ring) & 0x3FFFFu) >> 4, a2_wrap16 = (uint32_t)p.a2_groups * TC_G * (2048u >> 4);
     const uint32_t a2_end16 = a2_addr16 + a2_wrap16;
     const uint32_t b2_lo = ((smem_u32(sm.b2tile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
-    const bool corr = p.dbg_acc == nullptr;
+    const bool corr = LEAN || p.dbg_acc == nullptr;
     const uint32_t a2_groups = p.a2_groups;
     const bool wrap = p.n_mirror == 0;       // no mirror slots: a row's K steps may run past the end of the ring
     const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : 1u;
@@ -452,7 +462,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
             }
             // one job per sub-block: the row's operands are shared, the templates (B, B2) and the accumulator differ
             uint32_t b_lo = b_lo0, b2 = b2_lo;
-            for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub) {
+            for (uint32_t sb = 0; sb < (LEAN ? 1u : nsub); sb++, b_lo += b_sub, b2 += b2_sub) {
                 const uint32_t acc = mw + 2 * kb, d0 = acc * nbs;
                 TC_PROG(1 + mw, (2u << 24) | o);
                 if (!first_round) TT(2, mbar_wait<false>(t_empty + acc, kpar ^ 1, p.wd, 16 + mw, o, sm.prog));
@@ -640,11 +650,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         if (elect_one()) {
             TcSmem sm = {btile, ring, a2ring, b2tile, bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty, prog};
             const uint32_t mw = warp - 1;
-            switch (p.n_mirror ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
-                case 6: tc_mma_role<6>(p, sm, mw); break;
-                case 7: tc_mma_role<7>(p, sm, mw); break;
-                case 8: tc_mma_role<8>(p, sm, mw); break;
-                default: tc_mma_role<0>(p, sm, mw); break;
+            const bool lean = p.nsub == 1 && p.dbg_acc == nullptr;
+            switch (p.n_mirror && lean ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
+                case 6: tc_mma_role<6, true>(p, sm, mw); break;
+                case 7: tc_mma_role<7, true>(p, sm, mw); break;
+                case 8: tc_mma_role<8, true>(p, sm, mw); break;
+                default: tc_mma_role<0, false>(p, sm, mw); break;
             }
         }
         __syncwarp();
