@@ -864,24 +864,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 if (h1) tc_ld32(tb + u1 * 32, vb);
                 if (h0) tc_wait_ld32(va);
                 if (h1) tc_wait_ld32(vb);
-                if (!h2) {
-                    release();
-                    if (!no_screen) {
-                        if (h0) screen(va, u0);
-                        if (h1) screen(vb, u1);
-                    }
-                } else {
+                // a warp with more than two units screens its first two while the next two are in flight; the last
+                // (or only) pair is screened after the accumulator has been released.  One common tail for both cases
+                // keeps the code small (the single-warp roles are instruction-cache sensitive).
+                if (h2) {
                     if (!no_screen) screen(va, u0);
                     tc_ld32(tb + u2 * 32, va);
                     if (!no_screen) screen(vb, u1);
                     if (h3) tc_ld32(tb + u3 * 32, vb);
                     tc_wait_ld32(va);
                     if (h3) tc_wait_ld32(vb);
-                    release();
-                    if (!no_screen) {
-                        screen(va, u2);
-                        if (h3) screen(vb, u3);
-                    }
+                }
+                release();
+                if (!no_screen) {
+                    if (h2 || h0) screen(va, h2 ? u2 : u0);
+                    if (h2 ? h3 : h1) screen(vb, h2 ? u3 : u1);
                 }
                 if (tron) tacc[4] += clock64() - tseen_;       // ... to the end of the job (screens, candidates)
                 if (++kb == nbpp) kb = 0, kpar ^= 1;
