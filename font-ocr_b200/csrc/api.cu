@@ -433,7 +433,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         sa.n_h = ch.n_h;
         sa.inv_n_f = 1.0f / (float)(ch.n_w * ch.n_h);
         sa.sp = s.sp.as<uint32_t>();
-        sa.s2p = s.s2p.as<uint32_t>();
+        sa.s2p = tc ? nullptr : s.s2p.as<uint32_t>();   // the tcgen05 path recomputes s2_p for its few survivors
         sa.pf = s.pf.as<float>();
         sa.rn = tc ? nullptr : s.rn.as<double>();
         sa.spitch = g.spitch;

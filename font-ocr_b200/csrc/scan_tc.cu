@@ -921,7 +921,7 @@ struct CandArgs {
     const uint8_t *inv;
     size_t inv_page_stride;
     int pitch, n_w, n_h, np;
-    const uint32_t *sp, *s2p;
+    const uint32_t *sp;
     int spitch;
     size_t plane_page_stride;
     double n_d, thr_d;
@@ -946,17 +946,23 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             const uint8_t *p0 = a.inv + (size_t)c.page * a.inv_page_stride + (size_t)y * a.pitch + x;
             const int sh = (int)((uintptr_t)p0 & 3) * 8, nw4 = a.np >> 2;
             const uint32_t *prow = (const uint32_t *)((uintptr_t)p0 & ~(uintptr_t)3);
-            uint32_t acc = 0;
+            // ... and the window's sum of squares (ncc.rs:308) from the same words, bytes beyond n_w masked off: the
+            // tcgen05 path does not materialise an s2p plane (4 B per window of HBM traffic saved in window_stats)
+            uint32_t acc = 0, s2_p = 0;
             for (int ny = 0; ny < a.n_h; ny++, trow += nw4, prow += a.pitch >> 2) {
                 uint32_t lo = __ldg(prow);
                 for (int q = 0; q < nw4; q++) {
                     const uint32_t hi = __ldg(prow + q + 1);
-                    acc = __dp4a(__funnelshift_r(lo, hi, sh), __ldg(trow + q), acc);
+                    const uint32_t w = __funnelshift_r(lo, hi, sh);
+                    acc = __dp4a(w, __ldg(trow + q), acc);
+                    const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
+                    const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
+                    s2_p = __dp4a(wm, wm, s2_p);
                     lo = hi;
                 }
             }
             const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
-            const uint32_t s_p = a.sp[o], s2_p = a.s2p[o];
+            const uint32_t s_p = a.sp[o];
             const TplInfo ti = a.tpl[t];
             const double rn_p = patch_rnorm(s_p, s2_p, a.n_d);
             float sim;
@@ -1231,7 +1237,6 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         ca.n_h = tc.n_h;
         ca.np = tc.np;
         ca.sp = a.sp;
-        ca.s2p = a.s2p;
         ca.spitch = a.spitch;
         ca.plane_page_stride = a.plane_page_stride;
         ca.n_d = (double)(tc.n_w * tc.n_h);

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
                 const uint32_t s2 = vq[y * vp + x + n_w] - vq[y * vp + x];
                 const size_t o = plane + (size_t)gy * a.spitch + gx;
                 a.sp[o] = sp;
-                a.s2p[o] = s2;
+                if (a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
                 // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
                 const unsigned long long vint =
                     (unsigned long long)(n_w * n_h) * s2 - (unsigned long long)sp * sp;
