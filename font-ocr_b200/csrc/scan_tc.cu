@@ -951,14 +951,20 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             uint32_t acc = 0, s2_p = 0;
             for (int ny = 0; ny < a.n_h; ny++, trow += nw4, prow += a.pitch >> 2) {
                 uint32_t lo = __ldg(prow);
-                for (int q = 0; q < nw4; q++) {
-                    const uint32_t hi = __ldg(prow + q + 1);
-                    const uint32_t w = __funnelshift_r(lo, hi, sh);
-                    acc = __dp4a(w, __ldg(trow + q), acc);
-                    const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
-                    const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
-                    s2_p = __dp4a(wm, wm, s2_p);
-                    lo = hi;
+                for (int q0 = 0; q0 < nw4; q0 += 4) {
+                    const uint4 tv = __ldg((const uint4 *)(trow + q0));   // template rows are 16-byte aligned (np = 16 or 32)
+                    const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int q = q0 + k;
+                        const uint32_t hi = __ldg(prow + q + 1);
+                        const uint32_t w = __funnelshift_r(lo, hi, sh);
+                        acc = __dp4a(w, tw[k], acc);
+                        const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
+                        const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
+                        s2_p = __dp4a(wm, wm, s2_p);
+                        lo = hi;
+                    }
                 }
             }
             const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
