@@ -17,6 +17,7 @@
 // is hand written.  Latency class (microseconds per page): not on the roofline-critical path.
 #include <cub/cub.cuh>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -166,19 +167,38 @@ __global__ void __launch_bounds__(128) pp_emit(const PpSel *tmp, const uint32_t 
     }
 }
 
-struct Scratch {  // freed on scope exit
-    std::vector<void *> ptrs;
-    ~Scratch()
+// Scratch: grow-only device buffers cached per device (a cudaMalloc / cudaFree pair per buffer and call costs more
+// than the kernels, and cudaFree synchronises the device).  Calls on one device are serialised by the pool's mutex.
+struct Pool {
+    std::mutex mu;
+    struct Buf {
+        void *p = nullptr;
+        size_t cap = 0;
+    } bufs[16];
+    ~Pool()
     {
-        for (void *p : ptrs) cudaFree(p);
+        // device memory is reclaimed at process exit; calling cudaFree during static destruction is not safe
     }
+};
+static Pool g_pools[64];
+
+struct Scratch {
+    Pool &pool;
+    int next = 0;
+    explicit Scratch(Pool &p_) : pool(p_) {}
     template <class T>
     T *get(size_t n)
     {
-        void *p = nullptr;
-        if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr;
-        ptrs.push_back(p);
-        return (T *)p;
+        Pool::Buf &b = pool.bufs[next++];
+        const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+        if (b.cap < bytes) {
+            if (b.p) cudaFree(b.p);
+            b.p = nullptr, b.cap = 0;
+            const size_t want = bytes + bytes / 4;
+            if (cudaMalloc(&b.p, want) != cudaSuccess) return nullptr;
+            b.cap = want;
+        }
+        return (T *)b.p;
     }
 };
 
@@ -205,7 +225,10 @@ extern "C" int focr_process_hits_device(focr_ctx *ctx, const focr_match *matches
     PP_CU(cudaSetDevice(focr_internal_device(ctx)));
     cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
     const size_t cap = (size_t)n_pages * T * n_out;  // upper bound of the kept hits
-    Scratch sc;
+    const int dev = focr_internal_device(ctx);
+    if (dev < 0 || dev >= 64) return focr_internal_fail(FOCR_ERR_ARG, "focr_process_hits_device: device index");
+    std::lock_guard<std::mutex> lock(g_pools[dev].mu);
+    Scratch sc(g_pools[dev]);
     PpArgs a;
     a.m = matches_dev, a.counts = counts_dev, a.T = T, a.n_out = n_out, a.n_pages = n_pages;
     a.anchor = anchor_threshold, a.overlap = overlap;
