@@ -70,13 +70,10 @@ constexpr int TC_YSEG = 128;          // output rows per work item
 // setmaxnreg budget (the kernel is compiled for 72 registers x 896 threads): warps 0-3 (TMA producer, MMA issuer) keep
 // 64, Toeplitz warps 40, A2 warps 48, epilogue warps 88: 128 x (64 + 40 + 48) + 512 x 88 = 64512 (an exact fit of
 // 65536 made setmaxnreg.inc wait for ever)
-// Epilogue organisation: TC_TEAMS = 2 -- output rows alternate between two teams of 8 warps (a warp pays the per-row
-// overhead every second row, takes up to 4 units of a row); TC_TEAMS = 1 -- all 16 warps work on every row (<= 2 units
-// each, both loaded before the accumulator is released: the shortest hand-back).
-#ifndef FOCR_TC_TEAMS
-#define FOCR_TC_TEAMS 2
-#endif
-constexpr int TC_TEAMS = FOCR_TC_TEAMS;
+// Epilogue organisation: output rows alternate between two teams of 8 warps (a warp pays the per-row overhead every second
+// row and takes up to 4 of the row's 32-column units).  Measured alternative: all 16 warps on every row (<= 2 units each,
+// shortest hand-back) is slower, 0.464 vs 0.417 ms/page on the 224-column launch.
+constexpr int TC_TEAMS = 2;
 constexpr int TC_REGS_TOEPLITZ = 40;
 constexpr int TC_REGS_A2 = 48;
 constexpr int TC_REGS_EPILOGUE = 88;
@@ -781,17 +778,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         // has landed, before it is screened.
         const int e = warp - 12;
         const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
-        // TC_TEAMS == 2: team = which rows, sub = which units (sub, sub+2, ...).  TC_TEAMS == 1: every row, units sub, sub+4.
-        const int team = TC_TEAMS == 2 ? (e >> 2) & 1 : 0, sub = TC_TEAMS == 2 ? e >> 3 : e >> 2;
-        constexpr int USTEP = TC_TEAMS == 2 ? 2 : 4;
+        const int team = (e >> 2) & 1, sub = e >> 3;   // team = which rows, sub = which units of a row (sub, sub+2, ...)
+        constexpr int USTEP = 2;
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t nbpp = p.nbpp, nsub = p.nsub;
         const int nunits = p.nunits;
         const float T = p.dbg_acc ? 3.0e38f : TC_C0 - TC_MARGIN;
-        // next job of each pipeline (= issuing thread): accumulator pipe + 2*kb, phase kpar, as in tc_mma_role; a team
-        // only follows its own pipeline, with one team the warps follow both
-        uint32_t kb = 0, kpar = 0, kb_other = 0, kpar_other = 0;
+        uint32_t kb = 0, kpar = 0;                // the team's next job: accumulator team + 2*kb, phase kpar (as in tc_mma_role)
         Hit *my_list = p.cands + (size_t)(blockIdx.x * TC_LISTS_PER_CTA + e) * p.cand_cap;
         uint32_t my_count = 0;
         uint32_t orow0 = 0;                       // global output-row index of the current item's first row
@@ -801,23 +795,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int gx = it.x0 + m;
-            for (int y = it.ys0 + (TC_TEAMS == 2 ? (int)((team - orow0) & 1u) : 0); y < it.ys1; y += TC_TEAMS) {
-              const uint32_t pipe = TC_TEAMS == 2 ? (uint32_t)team : ((uint32_t)(y - it.ys0) + orow0) & 1u;
-              if (TC_TEAMS == 1 && pipe) {  // the row of the other pipeline: swap the counters in, and back out below
-                  uint32_t t0 = kb, t1 = kpar;
-                  kb = kb_other, kpar = kpar_other, kb_other = t0, kpar_other = t1;
-              }
+            for (int y = it.ys0 + (int)((team - orow0) & 1u); y < it.ys1; y += 2) {   // the team's rows of this item
               for (uint32_t sb = 0; sb < nsub; sb++) {
-                const uint32_t acc = pipe + 2 * kb;
+                const uint32_t acc = team + 2 * kb;
                 if (lane == 0) TC_PROG(warp, (uint32_t)(y - it.ys0) + orow0);
                 // ONE warp of the team polls the mbarrier (polling costs shared-memory bandwidth, which the tensor core's
                 // operand reads already use to ~80 %); its team-mates wait on a hardware named barrier
-                if (TC_TEAMS == 2) {
-                    if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
-                    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
-                } else {
-                    TT(0, mbar_wait(t_full + acc, kpar, p.wd, 20 + pipe, y, prog));
-                }
+                if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, kpar, p.wd, 20 + team, y, prog));
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
                 tc_fence_after();
                 const long long tseen_ = tron ? clock64() : 0;
                 const uint32_t tb = tlane + acc * p.nbs;
@@ -882,10 +867,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 }
                 if (tron) tacc[4] += clock64() - tseen_;       // ... to the end of the job (screens, candidates)
                 if (++kb == nbpp) kb = 0, kpar ^= 1;
-              }
-              if (TC_TEAMS == 1 && pipe) {
-                  uint32_t t0 = kb, t1 = kpar;
-                  kb = kb_other, kpar = kpar_other, kb_other = t0, kpar_other = t1;
               }
             }
             orow0 += it.ys1 - it.ys0;
