@@ -8,6 +8,7 @@ Layout (DESIGN.md has the full map):
   shard.py   page sharding across GPUs + host-side gather (no data-path collective)
   raster.py  FreeType template/glyph-bank producer (the (glyph, subpixel shift) raster cache)
   pages.py   synthetic page generator for the BASELINE configs
+  cli.py     flag-compatible `ncc` / `focr` front-ends (text, --csv, --raw)
 
 There is NO CPU fallback: anything that computes calls into libfocr_b200.so and raises if the
 library is missing.  The CPU restatement lives in oracle/ and is test infrastructure only.

@@ -360,6 +360,7 @@ class Template:
     offset_index: int
     offset: tuple          # the (x, y) subpixel offset BEFORE the y_offset correction
     pixels: np.ndarray     # u8 [n_h, n_w], A8 coverage
+    corrected_y: float = 0.0  # offset y + y_offset (ncc.rs:629), what --raw prints
 
 
 class TemplateBank:
@@ -381,7 +382,7 @@ class TemplateBank:
                 raise ValueError(box_size)  # the reference .unwrap()s the TryFrom error (ncc.rs:559)
             corrected = (off[0], f32(off[1] + y_off))  # ncc.rs:629
             for ch in alphabet:
-                self.templates.append(Template(ch, oi, off, render(font, ch, corrected, size, csize, padding)))
+                self.templates.append(Template(ch, oi, off, render(font, ch, corrected, size, csize, padding), corrected[1]))
 
     def __len__(self):
         return len(self.templates)
