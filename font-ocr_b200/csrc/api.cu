@@ -79,7 +79,7 @@ struct DevBuf {
 };
 
 struct Slot {  // everything one in-flight chunk of pages needs
-    DevBuf gray, inv, sp, s2p, pf, rn, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
+    DevBuf gray, inv, sp, s2p, pf, rn, sp2, pf2, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
     unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark,
                                          // [4..9] scan_tc watchdog (raised, tag, info, CTA, warp, parity)
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
@@ -182,7 +182,7 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slot) {
-        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.rowcount, &s.hits, &s.cands, &s.candcnt, &s.sel, &s.ycut,
+        for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.sp2, &s.pf2, &s.rowcount, &s.hits, &s.cands, &s.candcnt, &s.sel, &s.ycut,
                           &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
             b->release();
         if (s.flags_host) cudaFreeHost(s.flags_host);
@@ -392,6 +392,26 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     CU(s.hits.ensure(hit_cap * sizeof(Hit)));
     bool any_tc = false;
     for (auto &ch : b->classes) any_tc |= use_tc(c, ch);
+    // Box sizes of equal height that both go to the tcgen05 kernel share ONE statistics pass (the vertical sums and the row
+    // prefix sums do not depend on the width): partner[i] = j > i means "class i's pass also fills class j's planes".
+    const size_t n_cls = b->classes.size();
+    // The second plane set is ONE buffer, occupied from class i's pass until class j has been scanned: pairs never overlap.
+    std::vector<int> partner(n_cls, -1), filled_by(n_cls, -1);
+    for (size_t i = 0, busy_until = 0; i < n_cls; i++) {
+        const ClassHost &ci = b->classes[i];
+        if ((busy_until && i <= busy_until) || !use_tc(c, ci) || ci.n_w > g.r_w || ci.n_h > g.r_h) continue;
+        for (size_t j = i + 1; j < n_cls; j++) {
+            const ClassHost &cj = b->classes[j];
+            if (use_tc(c, cj) && cj.n_h == ci.n_h && cj.n_w <= g.r_w) {
+                partner[i] = (int)j, filled_by[j] = (int)i, busy_until = j;
+                break;
+            }
+        }
+    }
+    if (std::any_of(partner.begin(), partner.end(), [](int v) { return v >= 0; })) {
+        CU(s.sp2.ensure(g.plane_page_stride * nB * 4));
+        CU(s.pf2.ensure(g.plane_page_stride * nB * 4));
+    }
     const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
     if (any_tc) {
         CU(s.cands.ensure(n_lists * c->cand_per_warp * sizeof(Hit)));
@@ -420,10 +440,12 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     sink.T = T;
     sink.r_h = g.r_h;
 
-    for (auto &ch : b->classes) {
+    for (size_t ci = 0; ci < n_cls; ci++) {
+        const ClassHost &ch = b->classes[ci];
         if (ch.n_w > g.r_w || ch.n_h > g.r_h) continue;  // no window fits: no hits for these templates
         const bool tc = use_tc(c, ch);
-        StatsArgs sa;
+        const bool prefilled = filled_by[ci] >= 0;       // an earlier class of the same height computed these planes
+        StatsArgs sa{};
         sa.inv = s.inv.as<uint8_t>();
         sa.inv_page_stride = g.inv_page_stride;
         sa.pitch = g.pitch;
@@ -432,17 +454,24 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         sa.n_w = ch.n_w;
         sa.n_h = ch.n_h;
         sa.inv_n_f = 1.0f / (float)(ch.n_w * ch.n_h);
-        sa.sp = s.sp.as<uint32_t>();
+        sa.sp = prefilled ? s.sp2.as<uint32_t>() : s.sp.as<uint32_t>();
         sa.s2p = tc ? nullptr : s.s2p.as<uint32_t>();   // the tcgen05 path recomputes s2_p for its few survivors
-        sa.pf = s.pf.as<float>();
+        sa.pf = prefilled ? s.pf2.as<float>() : s.pf.as<float>();
         sa.rn = tc ? nullptr : s.rn.as<double>();
         sa.spitch = g.spitch;
         sa.plane_page_stride = g.plane_page_stride;
-        {
+        if (partner[ci] >= 0) {
+            const ClassHost &cp = b->classes[partner[ci]];
+            sa.n_w2 = cp.n_w;
+            sa.inv_n_f2 = 1.0f / (float)(cp.n_w * cp.n_h);
+            sa.sp2 = s.sp2.as<uint32_t>();
+            sa.pf2 = s.pf2.as<float>();
+        }
+        if (!prefilled) {
             StageTimer tm(c, FOCR_STAGE_STATS);
             CU(launch_window_stats(sa, nB, st));
+            c->launches++;
         }
-        c->launches++;
 
         ScanArgs a;
         a.inv = sa.inv;
@@ -686,7 +715,7 @@ extern "C" int focr_window_stats(focr_ctx *c, const uint8_t *page_gray_host, uin
     CU(cudaMemcpyAsync(s.gray.p, page_gray_host, page_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(launch_stage_invert(s.gray.as<uint8_t>(), page_bytes, r_w, s.inv.as<uint8_t>(), g.inv_page_stride, g.pitch, r_w,
                            r_h, 1, 1, c->stream));
-    StatsArgs sa;
+    StatsArgs sa{};
     sa.inv = s.inv.as<uint8_t>();
     sa.inv_page_stride = g.inv_page_stride;
     sa.pitch = g.pitch;
@@ -748,7 +777,7 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     CU(cudaMemsetAsync(s.rowcount.p, 0, (size_t)b->T * r_h * 4, st));
     CU(cudaMemsetAsync(s.flags.p, 0, 64, st));
     CU(cudaMemsetAsync(s.acc.p, 0, page_bytes * 4, st));
-    StatsArgs sa;
+    StatsArgs sa{};
     sa.inv = s.inv.as<uint8_t>();
     sa.inv_page_stride = g.inv_page_stride;
     sa.pitch = g.pitch;

@@ -16,6 +16,12 @@ struct StatsArgs {
     double *rn;  // may be NULL (only the SIMT scan and the parity probe need the f64 plane)
     int spitch;
     size_t plane_page_stride;
+    // optional second box of the SAME height (n_w2 != 0): its sp / pf planes come out of the same pass over the page
+    // (the vertical sums and the row prefix sums do not depend on the width)
+    int n_w2;
+    float inv_n_f2;
+    uint32_t *sp2;
+    float *pf2;
 };
 
 // what every scan kernel appends to

@@ -6,6 +6,7 @@
 //                                                       separable box sum gives the same exact integers)
 //   Searcher::prepare_for_size        ncc.rs:263-318   (s_p, patch_rnorm; start/end is only an optimisation
 //                                                       of the CPU scan and is not needed)
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
     extern __shared__ __align__(16) uint8_t smem[];
     const int n_w = a.n_w, n_h = a.n_h;
     const int x0 = blockIdx.x * ST_TW, y0 = blockIdx.y * ST_TH, page = blockIdx.z;
-    const int in_w = ST_TW + n_w - 1, in_h = ST_TH + n_h - 1;
+    const int in_w = ST_TW + max(n_w, a.n_w2) - 1, in_h = ST_TH + n_h - 1;
     const int twp = (in_w + 15) & ~15;      // shared row pitch in bytes
     const int vp = twp + 1;                 // prefix row pitch in words (odd-ish stride, +1 for E[in_w])
     uint8_t *pix = smem;
@@ -154,26 +155,28 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
     // phase 3
     {
         const int x = threadIdx.x, gx = x0 + x;
-        if (gx <= a.r_w - n_w) {
-            const double n_d = (double)(n_w * n_h);
-            const size_t plane = (size_t)page * a.plane_page_stride;
+        const size_t plane = (size_t)page * a.plane_page_stride;
+        auto emit = [&](const int w, const float inv_n_f, uint32_t *sp_out, float *pf_out, const bool extras) {
+            if (gx > a.r_w - w) return;
+            const double n_d = (double)(w * n_h);
             for (int y = 0; y < ST_TH; y++) {
                 const int gy = y0 + y;
                 if (gy > a.r_h - n_h) break;
-                const uint32_t sp = vs[y * vp + x + n_w] - vs[y * vp + x];
-                const uint32_t s2 = vq[y * vp + x + n_w] - vq[y * vp + x];
+                const uint32_t sp = vs[y * vp + x + w] - vs[y * vp + x];
+                const uint32_t s2 = vq[y * vp + x + w] - vq[y * vp + x];
                 const size_t o = plane + (size_t)gy * a.spitch + gx;
-                a.sp[o] = sp;
-                if (a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
+                sp_out[o] = sp;
+                if (extras && a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
                 // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
-                const unsigned long long vint =
-                    (unsigned long long)(n_w * n_h) * s2 - (unsigned long long)sp * sp;
+                const unsigned long long vint = (unsigned long long)(w * n_h) * s2 - (unsigned long long)sp * sp;
                 // prefilter operand of the tcgen05 epilogue: norm_p = sqrt(vint/n); +inf marks a
                 // constant window (rnorm_p = inf in the reference -> never a hit)
-                a.pf[o] = vint == 0ull ? __int_as_float(0x7f800000) : sqrtf((float)vint * a.inv_n_f);
-                if (a.rn) a.rn[o] = patch_rnorm(sp, s2, n_d);
+                pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : sqrtf((float)vint * inv_n_f);
+                if (extras && a.rn) a.rn[o] = patch_rnorm(sp, s2, n_d);
             }
-        }
+        };
+        emit(n_w, a.inv_n_f, a.sp, a.pf, true);
+        if (a.n_w2) emit(a.n_w2, a.inv_n_f2, a.sp2, a.pf2, false);
     }
 }
 
@@ -198,14 +201,14 @@ cudaError_t launch_stage_invert(const uint8_t *src, size_t src_page_stride, size
 cudaError_t launch_window_stats(const StatsArgs &a, int n_pages, cudaStream_t st)
 {
     static bool attr_set = false;
-    const size_t smem = window_stats_smem(a.n_w, a.n_h);
+    const size_t smem = window_stats_smem(std::max(a.n_w, a.n_w2), a.n_h);
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)window_stats_smem(MAX_TPL_W, MAX_TPL_H));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int xs = a.r_w - a.n_w + 1, ys = a.r_h - a.n_h + 1;
+    const int xs = a.r_w - std::min(a.n_w, a.n_w2 ? a.n_w2 : a.n_w) + 1, ys = a.r_h - a.n_h + 1;
     dim3 grid((xs + ST_TW - 1) / ST_TW, (ys + ST_TH - 1) / ST_TH, n_pages);
     window_stats_kernel<<<grid, ST_THREADS, smem, st>>>(a);
     return cudaGetLastError();
