@@ -156,19 +156,20 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
     {
         const int x = threadIdx.x, gx = x0 + x;
         const size_t plane = (size_t)page * a.plane_page_stride;
+        const int ny = min(ST_TH, a.r_h - n_h + 1 - y0);   // rows of this tile that hold windows
         auto emit = [&](const int w, const float inv_n_f, uint32_t *sp_out, float *pf_out, const bool extras) {
             if (gx > a.r_w - w) return;
             const double n_d = (double)(w * n_h);
-            for (int y = 0; y < ST_TH; y++) {
-                const int gy = y0 + y;
-                if (gy > a.r_h - n_h) break;
-                const uint32_t sp = vs[y * vp + x + w] - vs[y * vp + x];
-                const uint32_t s2 = vq[y * vp + x + w] - vq[y * vp + x];
-                const size_t o = plane + (size_t)gy * a.spitch + gx;
+            const uint32_t n_u = (uint32_t)(w * n_h);
+            size_t o = plane + (size_t)y0 * a.spitch + gx;
+            const uint32_t *e_s = vs + x, *e_q = vq + x;
+            for (int y = 0; y < ny; y++, o += a.spitch, e_s += vp, e_q += vp) {
+                const uint32_t sp = e_s[w] - e_s[0];
+                const uint32_t s2 = e_q[w] - e_q[0];
                 sp_out[o] = sp;
                 if (extras && a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
                 // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
-                const unsigned long long vint = (unsigned long long)(w * n_h) * s2 - (unsigned long long)sp * sp;
+                const unsigned long long vint = (unsigned long long)n_u * s2 - (unsigned long long)sp * sp;
                 // prefilter operand of the tcgen05 epilogue: norm_p = sqrt(vint/n); +inf marks a
                 // constant window (rnorm_p = inf in the reference -> never a hit)
                 pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : sqrtf((float)vint * inv_n_f);
