@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
                 const unsigned long long vint = (unsigned long long)n_u * s2 - (unsigned long long)sp * sp;
                 // prefilter operand of the tcgen05 epilogue: norm_p = sqrt(vint/n); +inf marks a
                 // constant window (rnorm_p = inf in the reference -> never a hit)
-                pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : sqrtf((float)vint * inv_n_f);
+                // (sqrt.approx: <= 2 ulp, i.e. < 2 units of the screen's 256-unit margin; the exact pass never reads pf)
+                float nrm;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nrm) : "f"((float)vint * inv_n_f));
+                pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : nrm;
                 if (extras && a.rn) a.rn[o] = patch_rnorm(sp, s2, n_d);
             }
         };
