@@ -46,6 +46,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "scan_tc.cuh"
@@ -929,28 +930,39 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             const uint32_t *prow = (const uint32_t *)((uintptr_t)p0 & ~(uintptr_t)3);
             // ... and the window's sum of squares (ncc.rs:308) from the same words, bytes beyond n_w masked off: the
             // tcgen05 path does not materialise an s2p plane (4 B per window of HBM traffic saved in window_stats)
+            // (issued first: the statistics and the template record are random 4..32-byte reads whose latency then overlaps the rows)
+            const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
+            const uint32_t s_p = __ldg(a.sp + o);
+            const TplInfo ti = a.tpl[t];
             uint32_t acc = 0, s2_p = 0;
-            for (int ny = 0; ny < a.n_h; ny++, trow += nw4, prow += a.pitch >> 2) {
-                uint32_t lo = __ldg(prow);
-                for (int q0 = 0; q0 < nw4; q0 += 4) {
-                    const uint4 tv = __ldg((const uint4 *)(trow + q0));   // template rows are 16-byte aligned (np = 16 or 32)
-                    const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+            const int pitch4 = a.pitch >> 2;
+            auto rows = [&](auto nw4_c) {   // nw4_c: words per template row as a compile-time constant (0: run-time nw4)
+                constexpr int NW4 = decltype(nw4_c)::value;
+                const int n4 = NW4 ? NW4 : nw4;
+#pragma unroll 4
+                for (int ny = 0; ny < a.n_h; ny++, trow += n4, prow += pitch4) {
+                    uint32_t lo = __ldg(prow);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int q = q0 + k;
-                        const uint32_t hi = __ldg(prow + q + 1);
-                        const uint32_t w = __funnelshift_r(lo, hi, sh);
-                        acc = __dp4a(w, tw[k], acc);
-                        const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
-                        const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
-                        s2_p = __dp4a(wm, wm, s2_p);
-                        lo = hi;
+                    for (int q0 = 0; q0 < n4; q0 += 4) {
+                        const uint4 tv = __ldg((const uint4 *)(trow + q0));   // template rows are 16-byte aligned (np = 16 or 32)
+                        const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const int q = q0 + k;
+                            const uint32_t hi = __ldg(prow + q + 1);
+                            const uint32_t w = __funnelshift_r(lo, hi, sh);
+                            acc = __dp4a(w, tw[k], acc);
+                            const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
+                            const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
+                            s2_p = __dp4a(wm, wm, s2_p);
+                            lo = hi;
+                        }
                     }
                 }
-            }
-            const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
-            const uint32_t s_p = a.sp[o];
-            const TplInfo ti = a.tpl[t];
+            };
+            if (nw4 == 4) rows(std::integral_constant<int, 4>{});
+            else if (nw4 == 8) rows(std::integral_constant<int, 8>{});
+            else rows(std::integral_constant<int, 0>{});
             const double rn_p = patch_rnorm(s_p, s2_p, a.n_d);
             float sim;
             if (ncc_exact(acc, s_p, rn_p, ti.s_n, ti.n_recip, ti.rnorm_n, a.thr_d, &sim)) {
