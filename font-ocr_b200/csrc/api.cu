@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -622,19 +623,26 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
     const uint32_t T = b->T;
     for (int attempt = 0; attempt < 6; attempt++) {
         const uint32_t B = pick_chunk(b, g, n_pages, c->hits_per_page);
-        std::vector<uint32_t> chunk_slot;
+        // chunk schedule {first page, pages}: the first chunks ramp up 2, 4, 8, .. B so that the kernels start after the
+        // H2D of two pages instead of a whole chunk (the copy of chunk i+1, twice the size, still hides behind chunk i)
+        std::vector<std::pair<uint32_t, uint32_t>> chunks;
+        for (uint32_t p0 = 0, sz = std::min<uint32_t>(2, B); p0 < n_pages; sz = std::min(B, sz * 2)) {
+            const uint32_t nB = std::min(sz, n_pages - p0);
+            chunks.emplace_back(p0, nB);
+            p0 += nB;
+        }
         bool redo = false;
         uint32_t ci = 0;
         // software pipeline over chunks: H2D of chunk i+1 overlaps the kernels of chunk i,
         // D2H of chunk i overlaps the kernels of chunk i+1
-        for (uint32_t p0 = 0; p0 < n_pages; p0 += B, ci++) {
-            const uint32_t nB = std::min(B, n_pages - p0);
+        for (; ci < chunks.size(); ci++) {
+            const uint32_t p0 = chunks[ci].first, nB = chunks[ci].second;
             Slot &s = c->slot[ci & 1];
             if (ci >= 2) {  // the slot's previous chunk must be fully drained before its buffers are reused
                 CU(cudaEventSynchronize(s.ev_d2h));
                 if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
             if (int wrc = chunk_watchdog(s)) return wrc;
-                if (chunk_overflowed(c, s, std::min(B, n_pages - (p0 - 2 * B)))) {
+                if (chunk_overflowed(c, s, chunks[ci - 2].second)) {
                     redo = true;
                     break;
                 }
@@ -672,8 +680,7 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
                 Slot &s = c->slot[k & 1];
                 if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
             if (int wrc = chunk_watchdog(s)) return wrc;
-                const uint32_t nB = std::min(B, n_pages - k * B);
-                if (chunk_overflowed(c, s, nB)) redo = true;
+                if (chunk_overflowed(c, s, chunks[k].second)) redo = true;
             }
         }
         if (!redo) return FOCR_OK;
