@@ -80,6 +80,8 @@ def _ncc_parser():
     ap.add_argument("--raw", action="store_true")
     ap.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
     ap.add_argument("--batch", type=int, default=16, help="(extension) pages per GPU batch")
+    ap.add_argument("--max-matches", type=int, default=1024,
+                    help="(extension) hits kept per template and page; the reference's MAX_MATCHES is 1024 (ncc.rs:31)")
     return ap
 
 
@@ -130,7 +132,7 @@ def ncc_main(argv=None, out=None) -> int:
     images = [load_luma8(p) for p in args.img]
     letters = bank_h.letters()
     tsize = [t.pixels.shape[::-1] for t in bank_h.templates]
-    T, n_out = len(bank_h), ncc.MAX_MATCHES
+    T, n_out = len(bank_h), args.max_matches
     ctx = ncc.Context(args.device)
     bank = ncc.Bank(ctx, [t.pixels for t in bank_h.templates])
     dev = torch.device("cuda", args.device)

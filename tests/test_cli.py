@@ -38,6 +38,7 @@ def test_flags_mirror_the_reference(pkg):
     assert (a.x_bits, a.y_bits, a.threshold, a.anchor_threshold, a.overlap, a.box_size, a.x_padding, a.csv, a.raw) == \
            (0, 0, 0.8, 0.95, 5, "alphabet", 0, False, False)
     assert a.alphabet == pkg.raster.NCC_DEFAULT_ALPHABET and a.img == ["a.png", "b.png"]
+    assert a.max_matches == 1024   # ncc.rs:31 unless the caller lifts it explicitly
     f = cli._focr_parser().parse_args(["-i", "a.png", "-f", "F", "-t", "13", "-w", "608", "--line-height", "12",
                                        "--line-advance", "15"])
     assert (f.x, f.y, f.kerning, f.width, f.line_height, f.line_advance) == (0, 0, 1.0, 608, 12, 15)
