@@ -12,6 +12,8 @@
 // the argmin (with the reference's first-minimum tie-break) is decided by the exact integer
 // Sum_box(g*(g - 2*ref)).  One warp walks one line: lanes score different glyphs of a cell in parallel,
 // the pen walk itself is sequential (the advance depends on the chosen glyph).
+#include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -206,6 +208,39 @@ extern "C" void focr_glyph_bank_destroy(focr_glyph_bank *b)
     delete b;
 }
 
+// Grow-only scratch per device (device buffers + pinned staging for the results): a cudaMalloc / cudaFree pair per buffer
+// and call cost more than the decode kernel (12 ms of a 31 ms call for 32 pages), and cudaFree synchronises the device.
+namespace {
+struct DecodeScratch {
+    std::mutex mu;
+    void *dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t dev_cap[4] = {0, 0, 0, 0};
+    void *host[2] = {nullptr, nullptr};
+    size_t host_cap[2] = {0, 0};
+    void *dev_buf(int i, size_t want)
+    {
+        if (want > dev_cap[i]) {
+            if (dev[i]) cudaFree(dev[i]);
+            dev[i] = nullptr, dev_cap[i] = 0;
+            if (cudaMalloc(&dev[i], want + want / 4) != cudaSuccess) return nullptr;
+            dev_cap[i] = want + want / 4;
+        }
+        return dev[i];
+    }
+    void *host_buf(int i, size_t want)
+    {
+        if (want > host_cap[i]) {
+            if (host[i]) cudaFreeHost(host[i]);
+            host[i] = nullptr, host_cap[i] = 0;
+            if (cudaHostAlloc(&host[i], want + want / 4, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            host_cap[i] = want + want / 4;
+        }
+        return host[i];
+    }
+};
+DecodeScratch g_decode_scratch[64];
+}  // namespace
+
 extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t *pages_host,
                                  size_t page_stride, uint32_t r_w, uint32_t r_h, uint32_t n_pages, uint32_t x_start,
                                  uint32_t y_start, uint32_t width, uint32_t line_height, uint32_t line_advance,
@@ -231,22 +266,36 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
     uint32_t *d_cells = nullptr;
     unsigned int *d_err = nullptr;
     const size_t n_lines_tot = (size_t)n_pages * max_lines;
-    FCU(cudaMalloc((void **)&d_pages, (size_t)r_w * r_h * n_pages));
-    FCU(cudaMalloc((void **)&d_glyphs, n_lines_tot * max_cells * 2));
-    FCU(cudaMalloc((void **)&d_cells, n_lines_tot * 4));
-    FCU(cudaMalloc((void **)&d_err, 4));
+    // Only the band the rectangles can touch goes to the device: columns [x_start, x_start+width) and rows from y_start
+    // (crop_imm's clamping, main.rs:201-203, applied once here); the kernel sees it as a page of its own with x_start =
+    // y_start = 0.  For BASELINE config 4 that is 608 of 2480 columns: 4x less H2D traffic, which is what bounds this path.
+    const uint32_t bx = std::min(x_start, r_w), by = std::min(y_start, r_h);
+    const uint32_t bw = std::min(width, r_w - bx), bh = r_h - by;
+    const size_t band_bytes = (size_t)bw * bh;
+    DecodeScratch &sc = g_decode_scratch[focr_internal_device(ctx) & 63];
+    std::lock_guard<std::mutex> lock(sc.mu);   // calls on one device share the scratch
+    d_pages = (uint8_t *)sc.dev_buf(0, std::max<size_t>(band_bytes * n_pages, 1));
+    d_glyphs = (uint16_t *)sc.dev_buf(1, n_lines_tot * max_cells * 2);
+    d_cells = (uint32_t *)sc.dev_buf(2, n_lines_tot * 4);
+    d_err = (unsigned int *)sc.dev_buf(3, 4);
+    uint16_t *g = (uint16_t *)sc.host_buf(0, n_lines_tot * max_cells * 2);
+    uint32_t *c = (uint32_t *)sc.host_buf(1, n_lines_tot * 4 + 4);
+    if (!d_pages || !d_glyphs || !d_cells || !d_err || !g || !c)
+        return focr_internal_fail(FOCR_ERR_NOMEM, "focr_decode_pages: scratch allocation failed");
     FCU(cudaMemsetAsync(d_cells, 0xFF, n_lines_tot * 4, st));
     FCU(cudaMemsetAsync(d_err, 0, 4, st));
-    FCU(cudaMemcpy2DAsync(d_pages, (size_t)r_w * r_h, pages_host, page_stride, (size_t)r_w * r_h, n_pages,
-                          cudaMemcpyHostToDevice, st));
+    if (band_bytes)
+        for (uint32_t p = 0; p < n_pages; p++)
+            FCU(cudaMemcpy2DAsync(d_pages + p * band_bytes, bw, pages_host + p * page_stride + (size_t)by * r_w + bx, r_w, bw,
+                                  bh, cudaMemcpyHostToDevice, st));
     DecodeArgs a;
     a.pages = d_pages;
-    a.page_stride = (size_t)r_w * r_h;
-    a.r_w = r_w;
-    a.r_h = r_h;
+    a.page_stride = band_bytes;
+    a.r_w = bw;
+    a.r_h = bh;
     a.n_pages = n_pages;
-    a.x_start = x_start;
-    a.y_start = y_start;
+    a.x_start = 0;
+    a.y_start = 0;
     a.width = width;
     a.line_height = line_height;
     a.line_advance = line_advance;
@@ -265,17 +314,11 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
     focr_decode_kernel<<<grid, FD_WARPS * 32, strip * FD_WARPS, st>>>(a);
     FCU(cudaGetLastError());
     focr_internal_count_launch(ctx, 1);
-    std::vector<uint16_t> g(n_lines_tot * max_cells);
-    std::vector<uint32_t> c(n_lines_tot);
-    unsigned int err = 0;
-    FCU(cudaMemcpyAsync(g.data(), d_glyphs, g.size() * 2, cudaMemcpyDeviceToHost, st));
-    FCU(cudaMemcpyAsync(c.data(), d_cells, c.size() * 4, cudaMemcpyDeviceToHost, st));
-    FCU(cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st));
+    FCU(cudaMemcpyAsync(g, d_glyphs, n_lines_tot * max_cells * 2, cudaMemcpyDeviceToHost, st));
+    FCU(cudaMemcpyAsync(c, d_cells, n_lines_tot * 4, cudaMemcpyDeviceToHost, st));
+    FCU(cudaMemcpyAsync(c + n_lines_tot, d_err, 4, cudaMemcpyDeviceToHost, st));
     FCU(cudaStreamSynchronize(st));
-    cudaFree(d_pages);
-    cudaFree(d_glyphs);
-    cudaFree(d_cells);
-    cudaFree(d_err);
+    const unsigned int err = c[n_lines_tot];
     if (err) return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: a line needs more than max_cells cells");
     // compact like decode_image: skip all-white strips, stop at the first empty text (main.rs:205-216)
     for (uint32_t p = 0; p < n_pages; p++) {
