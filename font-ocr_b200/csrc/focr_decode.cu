@@ -12,7 +12,11 @@
 // the argmin (with the reference's first-minimum tie-break) is decided by the exact integer
 // Sum_box(g*(g - 2*ref)).  One warp walks one line: lanes score different glyphs of a cell in parallel,
 // the pen walk itself is sequential (the advance depends on the chosen glyph).
+// The device copy of the bank pads every bitmap row to a multiple of 4 bytes (zeros) at a 4-byte-aligned offset, so that a
+// row that is not clipped horizontally is scored four pixels at a time: Sum(g*g) and Sum(g*ref) with __dp4a on the bank
+// word and the byte-shifted strip word.  Horizontally clipped cells (a line's first / last glyph) take the per-pixel loop.
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -45,7 +49,7 @@ struct DecodeArgs {
 
 __global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_kernel(DecodeArgs a)
 {
-    extern __shared__ uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];   // FD_WARPS strips + 16 bytes (the word loads may run past the last strip)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t line = blockIdx.x * FD_WARPS + warp;
     const uint32_t page = blockIdx.y;
@@ -94,12 +98,33 @@ __global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_kernel(DecodeArgs a
             const int bx0 = max(0, -dx), bx1 = min((int)gr.w, (int)w - dx);
             const int by0 = max(0, -dy), by1 = min((int)gr.h, (int)h - dy);
             int score = 0;
-            for (int by = by0; by < by1; by++) {
-                const uint8_t *brow = bm + by * gr.w;
-                const uint8_t *rrow = ref + (dy + by) * w + dx;
-                for (int bx = bx0; bx < bx1; bx++) {
-                    const int gv = brow[bx], rv = rrow[bx];
-                    score += gv * (gv - 2 * rv);
+            const int pitch = (gr.w + 3) & ~3;       // device bank: rows padded with zeros to whole words
+            if (bx0 == 0 && bx1 == (int)gr.w) {
+                const int nwords = pitch >> 2;
+                for (int by = by0; by < by1; by++) {
+                    const uint32_t *brow = (const uint32_t *)(bm + by * pitch);
+                    const uintptr_t ra = (uintptr_t)(ref + (dy + by) * (int)w + dx);   // the strip bytes under this bitmap row
+                    const uint32_t *rw = (const uint32_t *)(ra & ~(uintptr_t)3);
+                    const int sh = (int)(ra & 3) * 8;
+                    uint32_t lo = rw[0];
+                    uint32_t g2 = 0, gr_dot = 0;
+                    for (int q = 0; q < nwords; q++) {
+                        const uint32_t hi = rw[q + 1];
+                        const uint32_t gw = __ldg(brow + q);
+                        g2 = __dp4a(gw, gw, g2);
+                        gr_dot = __dp4a(gw, __funnelshift_r(lo, hi, sh), gr_dot);   // padding bytes of gw are 0
+                        lo = hi;
+                    }
+                    score += (int)g2 - 2 * (int)gr_dot;
+                }
+            } else {
+                for (int by = by0; by < by1; by++) {
+                    const uint8_t *brow = bm + by * pitch;
+                    const uint8_t *rrow = ref + (dy + by) * w + dx;
+                    for (int bx = bx0; bx < bx1; bx++) {
+                        const int gv = brow[bx], rv = rrow[bx];
+                        score += gv * (gv - 2 * rv);
+                    }
                 }
             }
             if (score < best_score) {  // within a lane glyph indices ascend: strict < keeps the first minimum
@@ -188,11 +213,24 @@ extern "C" int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size
     b->ctx = ctx;
     b->n_glyphs = n_glyphs;
     b->origin_x = (float)origin_x;
-    FCU(cudaMalloc((void **)&b->pixels, n_pixel_bytes ? n_pixel_bytes : 1));
+    // device copy: every bitmap row padded with zeros to a multiple of 4 bytes, every bitmap at a 4-byte-aligned offset
+    std::vector<focr_glyph_raster> rs(rasters, rasters + (size_t)n_glyphs * 64);
+    size_t total = 0;
+    for (auto &r : rs) total += (size_t)((r.w + 3) & ~3) * r.h;
+    std::vector<uint8_t> padded(total ? total : 4, 0);
+    size_t off = 0;
+    for (size_t i = 0; i < rs.size(); i++) {
+        const size_t pitch = (size_t)((rs[i].w + 3) & ~3);
+        for (uint32_t y = 0; y < rs[i].h; y++)
+            memcpy(padded.data() + off + y * pitch, pixels + rasters[i].offset + (size_t)y * rs[i].w, rs[i].w);
+        rs[i].offset = off;
+        off += pitch * rs[i].h;
+    }
+    FCU(cudaMalloc((void **)&b->pixels, padded.size()));
     FCU(cudaMalloc((void **)&b->rasters, (size_t)n_glyphs * 64 * sizeof(focr_glyph_raster)));
     FCU(cudaMalloc((void **)&b->advance, n_glyphs * sizeof(float)));
-    FCU(cudaMemcpy(b->pixels, pixels, n_pixel_bytes, cudaMemcpyHostToDevice));
-    FCU(cudaMemcpy(b->rasters, rasters, (size_t)n_glyphs * 64 * sizeof(focr_glyph_raster), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(b->pixels, padded.data(), padded.size(), cudaMemcpyHostToDevice));
+    FCU(cudaMemcpy(b->rasters, rs.data(), rs.size() * sizeof(focr_glyph_raster), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(b->advance, advance_px, n_glyphs * sizeof(float), cudaMemcpyHostToDevice));
     *out = b;
     return FOCR_OK;
@@ -309,9 +347,9 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
     a.glyphs = d_glyphs;
     a.n_cells = d_cells;
     a.error = d_err;
-    FCU(cudaFuncSetAttribute(focr_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    FCU(cudaFuncSetAttribute(focr_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     dim3 grid((max_lines + FD_WARPS - 1) / FD_WARPS, n_pages);
-    focr_decode_kernel<<<grid, FD_WARPS * 32, strip * FD_WARPS, st>>>(a);
+    focr_decode_kernel<<<grid, FD_WARPS * 32, strip * FD_WARPS + 16, st>>>(a);
     FCU(cudaGetLastError());
     focr_internal_count_launch(ctx, 1);
     FCU(cudaMemcpyAsync(g, d_glyphs, n_lines_tot * max_cells * 2, cudaMemcpyDeviceToHost, st));
