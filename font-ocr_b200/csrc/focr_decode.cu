@@ -30,7 +30,13 @@ struct GlyphBankDev {
     const focr_glyph_raster *rasters;  // [n_glyphs][64]
     const float *advance_px;           // [n_glyphs]
     uint32_t n_glyphs;
+    // row tasks: for every 26.6 phase the bitmap rows of all glyphs, in glyph order, as
+    // {byte offset of the row in `pixels`, glyph | w << 16, (u16)left | (u16)(top + row) << 16, 0}
+    const uint4 *tasks;                // [task_off[64]]
+    const uint32_t *task_off;          // [65]
 };
+
+constexpr uint32_t FD_MAX_SCORES = 256;   // glyphs per bank the row-task path keeps scores for (per warp, shared memory)
 
 constexpr int FD_WARPS = 4;  // lines per block
 
@@ -65,6 +71,10 @@ __global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_kernel(DecodeArgs a
     }
     // stage the inverted strip (main.rs:150) in shared memory
     uint8_t *ref = smem + (size_t)warp * a.width * a.line_height;
+    // per-warp glyph scores of the row-task path, behind the strips (16-byte aligned); nullptr: per-glyph path
+    int *scores = a.bank.tasks ? (int *)(smem + (((size_t)FD_WARPS * a.width * a.line_height + 16 + 15) & ~(size_t)15)) +
+                                     (size_t)warp * FD_MAX_SCORES
+                               : nullptr;
     const uint8_t *src = a.pages + (size_t)page * a.page_stride + (size_t)ys * a.r_w + xs;
     uint32_t any_ink = 0;
     for (uint32_t i = lane; i < w * h; i += 32) {
@@ -90,6 +100,55 @@ __global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_kernel(DecodeArgs a
         const int dint = d26 >> 6, frac = d26 & 63;
         int best_score = 0x7fffffff;
         uint32_t best_g = 0xFFFFFFFFu;
+        if (scores) {
+            // Row tasks: the lanes share the bitmap ROWS of all glyphs of this phase evenly (a lane per row, ~23 rows each
+            // for a 67-glyph alphabet) instead of whole glyphs (2-3 glyphs of very different sizes per lane: half of the
+            // lanes idle); a row's partial score goes to the glyph's slot with a shared-memory atomic.
+            for (uint32_t g = lane; g < a.bank.n_glyphs; g += 32) scores[g] = 0;
+            __syncwarp();
+            const uint32_t t0 = a.bank.task_off[frac], t1 = a.bank.task_off[frac + 1];
+            for (uint32_t t = t0 + lane; t < t1; t += 32) {
+                const uint4 tk = __ldg(a.bank.tasks + t);
+                const uint32_t g = tk.y & 0xFFFFu;
+                const int gw_ = (int)(tk.y >> 16);
+                const int dx = (int)(int16_t)(tk.z & 0xFFFFu) + dint, ry = (int)(int16_t)(tk.z >> 16);
+                if (ry < 0 || ry >= (int)h) continue;   // Canvas::blit_from clips the bitmap to the canvas
+                const int bx0 = max(0, -dx), bx1 = min(gw_, (int)w - dx);
+                const uint8_t *brow8 = a.bank.pixels + tk.x;
+                int part = 0;
+                if (bx0 == 0 && bx1 == gw_) {
+                    const uint32_t *brow = (const uint32_t *)brow8;
+                    const uintptr_t ra = (uintptr_t)(ref + ry * (int)w + dx);   // the strip bytes under this bitmap row
+                    const uint32_t *rw = (const uint32_t *)(ra & ~(uintptr_t)3);
+                    const int sh = (int)(ra & 3) * 8, nwords = (gw_ + 3) >> 2;
+                    uint32_t lo = rw[0], g2 = 0, gr_dot = 0;
+                    for (int q = 0; q < nwords; q++) {
+                        const uint32_t hi = rw[q + 1];
+                        const uint32_t gw = __ldg(brow + q);
+                        g2 = __dp4a(gw, gw, g2);
+                        gr_dot = __dp4a(gw, __funnelshift_r(lo, hi, sh), gr_dot);   // padding bytes of gw are 0
+                        lo = hi;
+                    }
+                    part = (int)g2 - 2 * (int)gr_dot;
+                } else {
+                    const uint8_t *rrow = ref + ry * (int)w + dx;
+                    for (int bx = bx0; bx < bx1; bx++) {
+                        const int gv = brow8[bx], rv = rrow[bx];
+                        part += gv * (gv - 2 * rv);
+                    }
+                }
+                if (part) atomicAdd(scores + g, part);
+            }
+            __syncwarp();
+            for (uint32_t g = lane; g < a.bank.n_glyphs; g += 32) {
+                const int score = scores[g];
+                if (score < best_score) {  // within a lane glyph indices ascend: strict < keeps the first minimum
+                    best_score = score;
+                    best_g = g;
+                }
+            }
+            __syncwarp();
+        } else
         for (uint32_t g = lane; g < a.bank.n_glyphs; g += 32) {
             const focr_glyph_raster gr = a.bank.rasters[(size_t)g * 64 + frac];
             const uint8_t *bm = a.bank.pixels + gr.offset;
@@ -190,6 +249,8 @@ struct focr_glyph_bank {
     float *advance;
     uint32_t n_glyphs;
     float origin_x;
+    uint4 *tasks;          // row tasks per phase (GlyphBankDev), nullptr when a bitmap is too large for the packing
+    uint32_t *task_off;
 };
 
 #define FCU(call)                                                                                          \
@@ -229,6 +290,33 @@ extern "C" int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size
     FCU(cudaMalloc((void **)&b->pixels, padded.size()));
     FCU(cudaMalloc((void **)&b->rasters, (size_t)n_glyphs * 64 * sizeof(focr_glyph_raster)));
     FCU(cudaMalloc((void **)&b->advance, n_glyphs * sizeof(float)));
+    // row tasks per phase, glyph order (GlyphBankDev::tasks)
+    b->tasks = nullptr, b->task_off = nullptr;
+    {
+        std::vector<uint4> tasks;
+        std::vector<uint32_t> toff(65, 0);
+        bool ok = padded.size() < (1ull << 32);
+        for (uint32_t ph = 0; ph < 64 && ok; ph++) {
+            toff[ph] = (uint32_t)tasks.size();
+            for (uint32_t g = 0; g < n_glyphs && ok; g++) {
+                const focr_glyph_raster &r = rs[(size_t)g * 64 + ph];
+                const uint32_t pitch = (r.w + 3u) & ~3u;
+                for (uint32_t y = 0; y < r.h; y++) {
+                    const int ry = (int)r.top + (int)y;
+                    if (ry < -32768 || ry > 32767) { ok = false; break; }
+                    tasks.push_back(make_uint4((uint32_t)(r.offset + (size_t)y * pitch), g | ((uint32_t)r.w << 16),
+                                               (uint32_t)(uint16_t)r.left | ((uint32_t)(uint16_t)(int16_t)ry << 16), 0u));
+                }
+            }
+        }
+        toff[64] = (uint32_t)tasks.size();
+        if (ok) {
+            FCU(cudaMalloc((void **)&b->tasks, std::max<size_t>(tasks.size(), 1) * sizeof(uint4)));
+            FCU(cudaMalloc((void **)&b->task_off, 65 * 4));
+            FCU(cudaMemcpy(b->tasks, tasks.data(), tasks.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+            FCU(cudaMemcpy(b->task_off, toff.data(), 65 * 4, cudaMemcpyHostToDevice));
+        }
+    }
     FCU(cudaMemcpy(b->pixels, padded.data(), padded.size(), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(b->rasters, rs.data(), rs.size() * sizeof(focr_glyph_raster), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(b->advance, advance_px, n_glyphs * sizeof(float), cudaMemcpyHostToDevice));
@@ -243,6 +331,8 @@ extern "C" void focr_glyph_bank_destroy(focr_glyph_bank *b)
     cudaFree(b->pixels);
     cudaFree(b->rasters);
     cudaFree(b->advance);
+    cudaFree(b->tasks);
+    cudaFree(b->task_off);
     delete b;
 }
 
@@ -290,7 +380,9 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
         return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: bad argument");
     if (page_stride < (size_t)r_w * r_h) return focr_internal_fail(FOCR_ERR_ARG, "page_stride smaller than a page");
     const size_t strip = (size_t)width * line_height;
-    if (strip * FD_WARPS > 200 * 1024 || strip == 0)
+    const bool row_tasks = bank->tasks && bank->n_glyphs <= FD_MAX_SCORES;
+    const size_t smem_bytes = ((strip * FD_WARPS + 16 + 15) & ~(size_t)15) + (row_tasks ? FD_WARPS * FD_MAX_SCORES * 4 : 0);
+    if (smem_bytes > 200 * 1024 + 16 || strip == 0)
         return focr_internal_fail(FOCR_ERR_UNSUPPORTED, "line rectangle too large for shared memory");
     FCU(cudaSetDevice(focr_internal_device(ctx)));
     cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
@@ -343,13 +435,15 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
     a.bank.rasters = bank->rasters;
     a.bank.advance_px = bank->advance;
     a.bank.n_glyphs = bank->n_glyphs;
+    a.bank.tasks = row_tasks ? bank->tasks : nullptr;
+    a.bank.task_off = bank->task_off;
     a.origin_x = bank->origin_x;
     a.glyphs = d_glyphs;
     a.n_cells = d_cells;
     a.error = d_err;
     FCU(cudaFuncSetAttribute(focr_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     dim3 grid((max_lines + FD_WARPS - 1) / FD_WARPS, n_pages);
-    focr_decode_kernel<<<grid, FD_WARPS * 32, strip * FD_WARPS + 16, st>>>(a);
+    focr_decode_kernel<<<grid, FD_WARPS * 32, smem_bytes, st>>>(a);
     FCU(cudaGetLastError());
     focr_internal_count_launch(ctx, 1);
     FCU(cudaMemcpyAsync(g, d_glyphs, n_lines_tot * max_cells * 2, cudaMemcpyDeviceToHost, st));
