@@ -133,13 +133,22 @@ struct ClassHost {
     uint32_t n_w, n_h, np;
     std::vector<uint32_t> index;
     DevBuf rows, index_dev;
-    TcClass tc;  // tcgen05 operand layout of this class (scan_tc.cu)
+    int group = -1;       // launch group of the tcgen05 kernel this box size belongs to
+    uint32_t group_pos = 0;  // index of the class's first template within the group
+};
+
+// launch group of the tcgen05 kernel (scan_tc.cu): one box size, or two box sizes of the same height that share the
+// correlation GEMM (their statistics ride in the two K chunks of the normalisation MMA)
+struct GroupHost {
+    int cls[2] = {-1, -1};
+    TcClass tc;
 };
 
 struct focr_bank {
     focr_ctx *ctx = nullptr;
     uint32_t T = 0;
     std::vector<ClassHost> classes;
+    std::vector<GroupHost> groups;
     std::vector<TplInfo> info;
     DevBuf info_dev;
 };
@@ -293,9 +302,13 @@ extern "C" int focr_bank_create(focr_ctx *c, const uint8_t *pixels, const uint64
         b->info[t].data_off = (uint32_t)b->classes[it->second].index.size() * h * b->classes[it->second].np;
         b->classes[it->second].index.push_back(t);
     }
-    for (auto &ch : b->classes) {
+    std::vector<std::vector<uint8_t>> rows_host(b->classes.size());
+    std::vector<std::vector<TplInfo>> cls_info(b->classes.size());
+    for (size_t ci = 0; ci < b->classes.size(); ci++) {
+        ClassHost &ch = b->classes[ci];
         // copy_needle_n_u8 (ncc.rs:925-935): rows zero-padded to np bytes
-        std::vector<uint8_t> rows((size_t)ch.index.size() * ch.n_h * ch.np, 0);
+        std::vector<uint8_t> &rows = rows_host[ci];
+        rows.assign((size_t)ch.index.size() * ch.n_h * ch.np, 0);
         for (size_t i = 0; i < ch.index.size(); i++) {
             const uint8_t *src = pixels + offsets[ch.index[i]];
             for (uint32_t y = 0; y < ch.n_h; y++)
@@ -305,12 +318,46 @@ extern "C" int focr_bank_create(focr_ctx *c, const uint8_t *pixels, const uint64
         CU(cudaMemcpy(ch.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice));
         CU(ch.index_dev.ensure(ch.index.size() * 4));
         CU(cudaMemcpy(ch.index_dev.p, ch.index.data(), ch.index.size() * 4, cudaMemcpyHostToDevice));
-        std::vector<TplInfo> cls_info;
-        for (uint32_t t : ch.index) cls_info.push_back(b->info[t]);
-        int rc = tc_class_build(ch.tc, rows.data(), ch.n_w, ch.n_h, ch.np, (uint32_t)ch.index.size(), ch.index.data(),
-                                cls_info.data());
+        for (uint32_t t : ch.index) cls_info[ci].push_back(b->info[t]);
+    }
+    // launch groups of the tcgen05 kernel: pair box sizes of equal height (and padded row width) whose boxes are small
+    // enough for the unscaled screen; everything else is a group of its own
+    const bool no_merge = getenv("FOCR_TC_NOMERGE") != nullptr;
+    auto src_of = [&](size_t ci) {
+        const ClassHost &ch = b->classes[ci];
+        return TcClassSrc{rows_host[ci].data(), ch.n_w, (uint32_t)ch.index.size(), ch.index.data(), cls_info[ci].data()};
+    };
+    auto mergeable = [](const ClassHost &ch) { return ch.np == 16 && ch.n_h <= 16 && ch.n_w * ch.n_h <= 256; };
+    for (size_t i = 0; i < b->classes.size(); i++) {
+        ClassHost &ci = b->classes[i];
+        if (ci.group >= 0) continue;
+        b->groups.emplace_back();
+        const int gi = (int)b->groups.size() - 1;
+        GroupHost &g = b->groups.back();
+        g.cls[0] = (int)i;
+        ci.group = gi;
+        ci.group_pos = 0;
+        int rc = 0;
+        if (!no_merge && mergeable(ci)) {
+            for (size_t j = i + 1; j < b->classes.size(); j++) {
+                ClassHost &cj = b->classes[j];
+                if (cj.group >= 0 || cj.n_h != ci.n_h || cj.np != ci.np || !mergeable(cj)) continue;
+                const TcClassSrc src[2] = {src_of(i), src_of(j)};
+                rc = tc_class_build(g.tc, src, 2, ci.n_h, ci.np);
+                if (rc == 0 && g.tc.supported) {
+                    g.cls[1] = (int)j;
+                    cj.group = gi;
+                    cj.group_pos = (uint32_t)ci.index.size();
+                }
+                break;
+            }
+        }
+        if (rc == 0 && g.cls[1] < 0) {
+            const TcClassSrc src = src_of(i);
+            rc = tc_class_build(g.tc, &src, 1, ci.n_h, ci.np);
+        }
         if (rc != 0) {
-            delete b;
+            focr_bank_destroy(b);
             return fail(FOCR_ERR_CUDA, "focr_bank_create: tcgen05 operand upload failed");
         }
     }
@@ -328,8 +375,8 @@ extern "C" void focr_bank_destroy(focr_bank *b)
     for (auto &ch : b->classes) {
         ch.rows.release();
         ch.index_dev.release();
-        tc_class_release(ch.tc);
     }
+    for (auto &g : b->groups) tc_class_release(g.tc);
     b->info_dev.release();
     delete b;
 }
@@ -361,10 +408,10 @@ static int make_geometry(uint32_t r_w, uint32_t r_h, uint32_t n_out, Geometry &g
     return FOCR_OK;
 }
 
-static bool use_tc(const focr_ctx *c, const ClassHost &ch)
+static bool use_tc(const focr_ctx *c, const focr_bank *b, const ClassHost &ch)
 {
     if (c->kernel == FOCR_KERNEL_SIMT) return false;
-    return tc_class_supported(ch.tc);
+    return tc_class_supported(b->groups[ch.group].tc);
 }
 
 // enqueue the whole device pipeline for nB pages that sit (gray or inverted) in device memory
@@ -374,45 +421,31 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
 {
     cudaStream_t st = c->stream;
     const uint32_t T = b->T;
-    bool any_simt = false;
+    bool any_simt = false, any_tc = false, any_pair = false;
     for (auto &ch : b->classes) {
-        if (c->kernel == FOCR_KERNEL_TCGEN05 && !tc_class_supported(ch.tc))
+        if (c->kernel == FOCR_KERNEL_TCGEN05 && !use_tc(c, b, ch))
             return fail(FOCR_ERR_UNSUPPORTED, "tcgen05 kernel does not support box " + std::to_string(ch.n_w) + "x" +
                                                   std::to_string(ch.n_h));
-        any_simt |= !use_tc(c, ch);
+        any_simt |= !use_tc(c, b, ch);
+        any_tc |= use_tc(c, b, ch);
     }
+    for (auto &gr : b->groups) any_pair |= gr.cls[1] >= 0;
     if (s.hits_per_page < c->hits_per_page) s.hits_per_page = c->hits_per_page;
     const size_t hit_cap = (size_t)s.hits_per_page * nB;
     const size_t PT = (size_t)nB * T;
     CU(s.inv.ensure(g.inv_page_stride * nB));
     CU(s.sp.ensure(g.plane_page_stride * nB * 4));
-    CU(s.s2p.ensure(g.plane_page_stride * nB * 4));
     CU(s.pf.ensure(g.plane_page_stride * nB * 4));
-    if (any_simt) CU(s.rn.ensure(g.plane_page_stride * nB * 8));
-    CU(s.rowcount.ensure(PT * g.r_h * 4));
-    CU(s.hits.ensure(hit_cap * sizeof(Hit)));
-    bool any_tc = false;
-    for (auto &ch : b->classes) any_tc |= use_tc(c, ch);
-    // Box sizes of equal height that both go to the tcgen05 kernel share ONE statistics pass (the vertical sums and the row
-    // prefix sums do not depend on the width): partner[i] = j > i means "class i's pass also fills class j's planes".
-    const size_t n_cls = b->classes.size();
-    // The second plane set is ONE buffer, occupied from class i's pass until class j has been scanned: pairs never overlap.
-    std::vector<int> partner(n_cls, -1), filled_by(n_cls, -1);
-    for (size_t i = 0, busy_until = 0; i < n_cls; i++) {
-        const ClassHost &ci = b->classes[i];
-        if ((busy_until && i <= busy_until) || !use_tc(c, ci) || ci.n_w > g.r_w || ci.n_h > g.r_h) continue;
-        for (size_t j = i + 1; j < n_cls; j++) {
-            const ClassHost &cj = b->classes[j];
-            if (use_tc(c, cj) && cj.n_h == ci.n_h && cj.n_w <= g.r_w) {
-                partner[i] = (int)j, filled_by[j] = (int)i, busy_until = j;
-                break;
-            }
-        }
+    if (any_simt) {   // only the SIMT kernel reads the sum-of-squares and f64 planes
+        CU(s.s2p.ensure(g.plane_page_stride * nB * 4));
+        CU(s.rn.ensure(g.plane_page_stride * nB * 8));
     }
-    if (std::any_of(partner.begin(), partner.end(), [](int v) { return v >= 0; })) {
+    if (any_tc && any_pair) {
         CU(s.sp2.ensure(g.plane_page_stride * nB * 4));
         CU(s.pf2.ensure(g.plane_page_stride * nB * 4));
     }
+    CU(s.rowcount.ensure(PT * g.r_h * 4));
+    CU(s.hits.ensure(hit_cap * sizeof(Hit)));
     const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
     if (any_tc) {
         CU(s.cands.ensure(n_lists * c->cand_per_warp * sizeof(Hit)));
@@ -441,11 +474,10 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     sink.T = T;
     sink.r_h = g.r_h;
 
-    for (size_t ci = 0; ci < n_cls; ci++) {
-        const ClassHost &ch = b->classes[ci];
-        if (ch.n_w > g.r_w || ch.n_h > g.r_h) continue;  // no window fits: no hits for these templates
-        const bool tc = use_tc(c, ch);
-        const bool prefilled = filled_by[ci] >= 0;       // an earlier class of the same height computed these planes
+    // One scan per launch group on the tcgen05 path (its one or two box sizes share a statistics pass: the vertical sums
+    // and the row prefix sums do not depend on the width), one per box size on the SIMT path.
+    auto scan_unit = [&](const ClassHost &ch, const ClassHost *ch2, const TcClass *tcg) -> int {
+        const bool tc = tcg != nullptr;
         StatsArgs sa{};
         sa.inv = s.inv.as<uint8_t>();
         sa.inv_page_stride = g.inv_page_stride;
@@ -455,25 +487,23 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         sa.n_w = ch.n_w;
         sa.n_h = ch.n_h;
         sa.inv_n_f = 1.0f / (float)(ch.n_w * ch.n_h);
-        sa.sp = prefilled ? s.sp2.as<uint32_t>() : s.sp.as<uint32_t>();
+        sa.sp = s.sp.as<uint32_t>();
         sa.s2p = tc ? nullptr : s.s2p.as<uint32_t>();   // the tcgen05 path recomputes s2_p for its few survivors
-        sa.pf = prefilled ? s.pf2.as<float>() : s.pf.as<float>();
+        sa.pf = s.pf.as<float>();
         sa.rn = tc ? nullptr : s.rn.as<double>();
         sa.spitch = g.spitch;
         sa.plane_page_stride = g.plane_page_stride;
-        if (partner[ci] >= 0) {
-            const ClassHost &cp = b->classes[partner[ci]];
-            sa.n_w2 = cp.n_w;
-            sa.inv_n_f2 = 1.0f / (float)(cp.n_w * cp.n_h);
+        if (ch2) {
+            sa.n_w2 = ch2->n_w;
+            sa.inv_n_f2 = 1.0f / (float)(ch2->n_w * ch2->n_h);
             sa.sp2 = s.sp2.as<uint32_t>();
             sa.pf2 = s.pf2.as<float>();
         }
-        if (!prefilled) {
+        {
             StageTimer tm(c, FOCR_STAGE_STATS);
             CU(launch_window_stats(sa, nB, st));
             c->launches++;
         }
-
         ScanArgs a;
         a.inv = sa.inv;
         a.inv_page_stride = g.inv_page_stride;
@@ -491,6 +521,8 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.s2p = sa.s2p;
         a.pf = sa.pf;
         a.rn = sa.rn;
+        a.sp2 = sa.sp2;
+        a.pf2 = sa.pf2;
         a.spitch = g.spitch;
         a.plane_page_stride = g.plane_page_stride;
         a.thr_d = (double)threshold;  // ncc.cpp:83
@@ -507,13 +539,29 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
             StageTimer tm(c, FOCR_STAGE_SCAN);
             if (tc) {
                 ExactStage hook(c);
-                CU(launch_scan_tc(ch.tc, a, nB, c->sm_count, st, &nl, nullptr, -1, &hook));
+                CU(launch_scan_tc(*tcg, a, nB, c->sm_count, st, &nl, nullptr, -1, &hook));
             }
             else
                 CU(launch_scan_simt(a, nB, st, &nl));
             tm.launches = nl;
         }
         c->launches += nl;
+        return FOCR_OK;
+    };
+    auto fits = [&](const ClassHost &ch) { return ch.n_w <= g.r_w && ch.n_h <= g.r_h; };  // else no window: no hits
+    for (auto &gr : b->groups) {
+        const ClassHost &c0 = b->classes[gr.cls[0]];
+        const ClassHost *c1 = gr.cls[1] >= 0 ? &b->classes[gr.cls[1]] : nullptr;
+        if (use_tc(c, b, c0)) {
+            // (a page narrower than the wider box: the group still runs, that box's windows are all flagged invalid)
+            if (!fits(c0) && !(c1 && fits(*c1))) continue;
+            if (int rc = scan_unit(c0, c1, &gr.tc)) return rc;
+        } else {
+            if (fits(c0))
+                if (int rc = scan_unit(c0, nullptr, nullptr)) return rc;
+            if (c1 && fits(*c1))
+                if (int rc = scan_unit(*c1, nullptr, nullptr)) return rc;
+        }
     }
 
     FinalizeArgs f;
@@ -837,13 +885,26 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
     a.acc_out = s.acc.as<uint32_t>();
     int nl = 0;
     if (c->kernel == FOCR_KERNEL_TCGEN05) {
-        // same probe through the tcgen05 kernel: the whole class runs, column `pos` is dumped from TMEM
-        if (!tc_class_supported(ch.tc)) return fail(FOCR_ERR_UNSUPPORTED, "tcgen05 kernel does not support this box");
-        a.cls.n_tpl = (uint32_t)ch.index.size();
-        a.cls.tpl_index = ch.index_dev.as<uint32_t>();
-        a.cls.rows = ch.rows.as<uint8_t>();
+        // same probe through the tcgen05 kernel: the template's whole launch group runs, its column is dumped from TMEM
+        const GroupHost &gr = b->groups[ch.group];
+        if (!tc_class_supported(gr.tc)) return fail(FOCR_ERR_UNSUPPORTED, "tcgen05 kernel does not support this box");
+        if (gr.cls[1] >= 0) {   // the A2 warps read the planes of both box sizes of the group
+            const ClassHost &c0 = b->classes[gr.cls[0]], &c1 = b->classes[gr.cls[1]];
+            if (c0.n_w > r_w || c1.n_w > r_w) return fail(FOCR_ERR_ARG, "template larger than the page");
+            CU(s.sp2.ensure(g.plane_page_stride * 4));
+            CU(s.pf2.ensure(g.plane_page_stride * 4));
+            sa.n_w = c0.n_w;
+            sa.inv_n_f = 1.0f / (float)(c0.n_w * c0.n_h);
+            sa.n_w2 = c1.n_w;
+            sa.inv_n_f2 = 1.0f / (float)(c1.n_w * c1.n_h);
+            sa.sp2 = s.sp2.as<uint32_t>();
+            sa.pf2 = s.pf2.as<float>();
+            CU(launch_window_stats(sa, 1, st));
+            a.sp2 = sa.sp2;
+            a.pf2 = sa.pf2;
+        }
         a.acc_out = nullptr;
-        CU(launch_scan_tc(ch.tc, a, 1, c->sm_count, st, &nl, s.acc.as<uint32_t>(), (int)pos));
+        CU(launch_scan_tc(gr.tc, a, 1, c->sm_count, st, &nl, s.acc.as<uint32_t>(), (int)(ch.group_pos + pos)));
     } else {
         CU(launch_scan_simt(a, 1, st, &nl));
     }

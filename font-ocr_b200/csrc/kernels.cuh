@@ -44,6 +44,8 @@ struct ScanArgs {
     const uint32_t *s2p;
     const float *pf;
     const double *rn;
+    const uint32_t *sp2 = nullptr;   // tcgen05 launch groups of two box sizes: the planes of the second one
+    const float *pf2 = nullptr;
     int spitch;
     size_t plane_page_stride;
     double thr_d;

@@ -33,10 +33,19 @@
 //    operation, so decisions and f32 scores are bit-identical to the CPU.  Nothing can be missed: every
 //    approximation errs towards MORE candidates.
 //
+//  * A launch covers the templates of one box size or of TWO box sizes of the same height: the correlation GEMM only
+//    sees zero-padded template rows, and the fp16 MMA's two 16-byte K chunks carry one set of window statistics each
+//    (a column's B2 entry is non-zero only in the chunk of its own box size).
+//  * A JOB = one output row x one sub-block of <= 256 columns (a launch has 1 or 2 sub-blocks per row).  Jobs walk a
+//    RING of TMEM accumulators (512 / columns per sub-block of them): ONE warp issues all jobs in order (converged, all
+//    its state in uniform registers), the tensor pipe executes them in order, two teams of 8 epilogue warps drain
+//    alternate jobs and hand the accumulator back before they screen their last chunks.  With three accumulators the
+//    hand-back chain (commit -> team wakes -> tcgen05.ld -> release -> issuer wakes) has two whole jobs of tensor time.
+//
 // Warp roles (one persistent CTA per SM over (page, x-strip, y-segment) items):
-//   warp 0     TMA producer of raw page rows         warps 1-2   MMA issuers (one elected thread each, alternate rows)
+//   warp 0     TMA producer of raw page rows         warp 1      MMA issuer (converged warp, elect.sync-guarded tcgen05)
 //   warp 3     TMEM alloc, otherwise idle            warps 4-7   Toeplitz expansion (one warp per row)
-//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-   epilogue (TC_EPI_GROUPS per TMEM lane quarter)
+//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-27 epilogue (2 teams x 2 per TMEM lane quarter)
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
@@ -56,8 +65,9 @@ namespace cg = cooperative_groups;
 namespace focr {
 
 constexpr int TC_EPI_GROUPS = 4;      // epilogue warps per TMEM lane quarter
-constexpr int TC_THREADS = 384 + 128 * TC_EPI_GROUPS;
-static_assert(TC_LISTS_PER_CTA == 4 * TC_EPI_GROUPS, "scan_tc.cuh: candidate lists per CTA = epilogue warps");
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_GROUPS;
+constexpr int TC_THREADS = 384 + 32 * TC_EPI_WARPS;
+static_assert(TC_LISTS_PER_CTA == TC_EPI_WARPS, "scan_tc.cuh: candidate lists per CTA = epilogue warps");
 static_assert(TC_EPI_GROUPS == 4, "the epilogue is written for 2 teams x 2 warps per lane quarter");
 constexpr int TC_G = 4;               // rows per pipeline group: one mbarrier handshake per 4 rows
 constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
@@ -67,14 +77,10 @@ constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side m
 constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: up to 4 groups x 4 output rows x 2 KB (2 for tall boxes)
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
-constexpr int TC_YSEG = 128;          // output rows per work item
+constexpr int TC_YSEG = 128;          // output rows per work item (fewer on small batches, see launch_scan_tc)
 // setmaxnreg budget (the kernel is compiled for 72 registers x 896 threads): warps 0-3 (TMA producer, MMA issuer) keep
 // 64, Toeplitz warps 40, A2 warps 48, epilogue warps 88: 128 x (64 + 40 + 48) + 512 x 88 = 64512 (an exact fit of
 // 65536 made setmaxnreg.inc wait for ever)
-// Epilogue organisation: output rows alternate between two teams of 8 warps (a warp pays the per-row overhead every second
-// row and takes up to 4 of the row's 32-column units).  Measured alternative: all 16 warps on every row (<= 2 units each,
-// shortest hand-back) is slower, 0.464 vs 0.417 ms/page on the 224-column launch.
-constexpr int TC_TEAMS = 2;
 constexpr int TC_REGS_TOEPLITZ = 40;
 constexpr int TC_REGS_A2 = 48;
 constexpr int TC_REGS_EPILOGUE = 88;
@@ -89,33 +95,35 @@ struct TcParams {
     const uint8_t *inv;
     size_t inv_page_stride;
     int pitch, r_w, r_h;
-    int n_w, n_h, np;
+    int n_w, n_w2, n_h, np;   // n_w2: width of the second box size (ncls == 2)
+    int ncls;          // box sizes in this launch group (1 or 2)
     int n_hp;          // page rows an output row needs (n_h rounded up to 2 when np == 16)
     int ksteps;        // tcgen05.mma kind::i8 per output row
     int nb;            // columns per launch = nsub * nbs
     int nsub;          // sub-blocks: jobs (accumulators) per output row
     int nunits;        // 32-column epilogue units per accumulator
     int nbs;           // columns per sub-block = N of the MMAs = TMEM column stride between accumulators (multiple of 32)
-    int nbuf;          // accumulators (even)
-    int nbpp;          // accumulators per pipeline (issuing thread + epilogue team) = nbuf / 2
+    int nbuf;          // accumulators in the ring: job k uses number k mod nbuf
     int ring;          // expanded-row ring slots = ring_groups * 4
     int ring_groups;
     int n_mirror;      // ring slots stored twice (see tc_mma_role); 0: the issue loop wraps every K step (np == 32)
     int a2_groups;     // groups of the A2 ring (<= TC_A2_GROUPS)
+    int a2_slot;       // bytes per A2 row: 2048 per box size
     int sshift;        // the templates of the B tile are ceil(t / 2^sshift): S is split at bit 10 instead of 6 (see A2 rows)
     int row_pitch;     // bytes per expanded row slot
     int n_entries;     // 16-byte entries per expanded row (128, or 144 for np == 32)
+    int yseg;          // output rows per work item
     const uint8_t *btile;     // [nsub][2*ksteps][nbs][16]
     uint32_t btile_bytes;
-    const float2 *colconst;   // [nb] {norm_n, s_n/n}; norm_n = +inf for padding / constant templates
+    const float4 *colconst;   // [nb] {norm_n, s_n/n, box size index, -}; norm_n = +inf for padding / constant templates
     float thr;
-    float bmax, amax;         // max over this launch's columns of s_n/n and max(thr*norm_n, 0)
-    uint32_t col_base;        // this launch's first column within the class (N-block * nb)
-    const uint32_t *sp;
-    const float *pf;
+    float bmax[2], amax[2];   // per box size: max over this launch's columns of s_n/n and max(thr*norm_n, 0)
+    uint32_t col_base;        // this launch's first column within the group (N-block * nb)
+    const uint32_t *sp[2];    // window statistics planes per box size
+    const float *pf[2];
     int spitch;
     size_t plane_page_stride;
-    Hit *cands;               // candidate lists, one PRIVATE list per epilogue warp: [grid*TC_LISTS_PER_CTA][cand_cap] {class column, y<<16|x, -, page}
+    Hit *cands;               // candidate lists, one PRIVATE list per epilogue warp: [grid*TC_LISTS_PER_CTA][cand_cap] {group column, y<<16|x, -, page}
     uint32_t cand_cap;        // entries per warp list
     unsigned int *cand_count; // [grid*TC_LISTS_PER_CTA] entries each warp produced (may exceed cand_cap -> the host grows the lists and retries)
     int n_pages, n_xstrips, n_ysegs;
@@ -126,7 +134,7 @@ struct TcParams {
                         // 1 epilogue skips the TMEM reads, 2 epilogue loads but does not screen, 4 no MMAs are issued,
                         // 8 A2 rows skip their global loads, 16 no Toeplitz expansion, 32 A2 rows skip their stores
     uint32_t *dbg_acc;  // parity probe: raw numerators of column dbg_col, [y*r_w+x]; disables the fp16 MMA
-    int dbg_col;
+    int dbg_col, dbg_xlast;   // dbg_xlast = r_w - (box width of that column)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -194,10 +202,9 @@ __device__ __noinline__ bool mbar_watchdog(unsigned int *wd, uint32_t tries, uin
 }
 
 template <bool HINT = true>
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
-                                          uint32_t info = 0, volatile uint32_t *prog = nullptr)
+__device__ __forceinline__ void mbar_wait_addr(const uint32_t addr, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
+                                               uint32_t info = 0, volatile uint32_t *prog = nullptr)
 {
-    const uint32_t addr = smem_u32(bar);
     uint32_t done, tries = 0;
     for (;;) {
         if (HINT)
@@ -220,6 +227,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsign
         if (wd && (++tries & 63u) == 0 && mbar_watchdog(wd, tries, tag, info, parity, addr, prog)) return;
     }
 }
+template <bool HINT = true>
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *wd = nullptr, uint32_t tag = 0,
+                                          uint32_t info = 0, volatile uint32_t *prog = nullptr)
+{
+    mbar_wait_addr<HINT>(smem_u32(bar), parity, wd, tag, info, prog);
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -231,21 +244,30 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
+// The issuing WARP walks its role converged (every value it computes is warp-uniform, so ptxas keeps descriptors and
+// loop state in uniform registers: no R2UR in the issue sequence); the tcgen05 instructions themselves are guarded by the
+// `leader` flag from elect.sync, which ptxas turns into ONE uniform-datapath instruction per warp (UTCIMMA / UTCHMMA /
+// UTCBAR).
+__device__ __forceinline__ uint32_t elect_flag()
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
+    uint32_t pred;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void tc_commit(uint32_t leader, uint32_t bar_addr)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_addr),
+        "r"(leader)
         : "memory");
 }
-// guarded variant for unrolled issue sequences: nothing is issued when guard == 0
+// nothing is issued when guard == 0
 __device__ __forceinline__ void tc_mma_i8_if(uint32_t guard, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate)
 {
@@ -258,13 +280,14 @@ __device__ __forceinline__ void tc_mma_i8_if(uint32_t guard, uint32_t d_tmem, ui
         : "memory");
 }
 // D = A*B (accumulate off): the fp16 MMA opens every output row and overwrites the previous row's result
-__device__ __forceinline__ void tc_mma_f16_overwrite(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
+__device__ __forceinline__ void tc_mma_f16_overwrite_if(uint32_t guard, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc)
+        "setp.ne.b32 q, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(guard)
         : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
@@ -287,6 +310,16 @@ __device__ __forceinline__ void tc_wait_ld32(uint32_t (&v)[32])
                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
                    "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31]));
+}
+// 16-column variant (the tail of a warp's column range): fills v[0..15]
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
 }
 __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
 {
@@ -340,8 +373,8 @@ __device__ __forceinline__ bool get_item(const TcParams &p, int idx, Item &it)
     const int r = idx - it.page * per_page;
     const int ys = r / p.n_xstrips, xs = r - ys * p.n_xstrips;
     it.x0 = xs * 128;
-    it.ys0 = 1 + ys * TC_YSEG;  // ncc.cpp:98: the scan starts at y = 1
-    it.ys1 = min(it.ys0 + TC_YSEG, p.r_h - p.n_h + 1);
+    it.ys0 = 1 + ys * p.yseg;  // ncc.cpp:98: the scan starts at y = 1
+    it.ys1 = min(it.ys0 + p.yseg, p.r_h - p.n_h + 1);
     return true;
 }
 
@@ -374,26 +407,25 @@ __device__ __forceinline__ void append_candidates(Hit *list, uint32_t cap, uint3
 }
 
 // ---------------------------------------------------------------------------------------------- MMA issuers
-struct TcSmem {
-    uint8_t *btile, *ring, *a2ring, *b2tile;
-    uint64_t *bar_btile, *a_full, *a_empty, *a2_full, *a2_empty, *t_full, *t_empty;
+struct TcSmem {   // shared-memory addresses (shared window, bytes) of the operands and barriers the issuing warp touches
+    uint32_t btile, ring, a2ring, b2tile;
+    uint32_t bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty;
     volatile uint32_t *prog;
 };
 
-// Two issuing threads (one elected lane of warp 1 and of warp 2): thread `mw` owns the output rows whose global
-// index has parity mw.  A single thread's dependent instruction stream (waits, descriptor arithmetic, R2UR,
-// UTCIMMA, commits) runs at ~6 cycles per instruction and cannot feed the tensor pipe alone; two can, and they
-// touch different accumulators, so their relative order is free.  With two accumulators thread mw, accumulator mw
-// and epilogue team mw form one independent pipeline.  A ring group goes back to its producer when BOTH threads
-// have moved past it: each commits to the group's "empty" barrier (count 2) once its next own output no longer
-// reads the group -- tcgen05.commit only tracks the MMAs of the committing thread.
+// ONE warp (warp 1) issues every job in order: job k (output row k / nsub, sub-block k % nsub) goes to accumulator
+// k mod nbuf.  The tensor pipe executes MMAs in issue order, so the warp only has to stay ahead of it: its per-job stream
+// is one wait (the accumulator's "empty" barrier, usually long since complete when the ring has three entries), 1 + KS
+// MMAs and one commit.  The row's operands (ring slots, A2 row) are shared by its jobs.
+// The warp runs CONVERGED and everything it computes depends only on kernel parameters and loop counters, so ptxas keeps
+// the whole role in uniform registers (descriptor arithmetic = UIADD3, no R2UR); `leader` (elect.sync) guards the
+// tcgen05 instructions, which are uniform-datapath instructions executed once per warp.
 // KS = K steps per output row as a compile-time constant (0: generic loop): the issue sequence is straight-line
 // code, and because the ring stores its first n_hp-1 slots twice, every descriptor of a row is the first one plus
 // a constant.
-// LEAN = the common case (one sub-block per row, no parity probe): the per-row instruction stream of this thread sets the
-// speed of the kernel (every ~10 instructions per row cost 1-2 %), so that case is compiled without the extras.
+// LEAN = no parity probe (the common case): the fp16 MMA is always issued, no run-time switches in the issue sequence.
 template <int KS, bool LEAN>
-__device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t mw)
+__device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t leader)
 {
     const uint32_t idesc8 = (2u << 4)                          // D format: S32
                             | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
@@ -403,7 +435,7 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const uint32_t idesc16 = (1u << 4)                         // D format: F32 (same TMEM columns, read as fp32)
                              | (0u << 7) | (0u << 10)          // A, B: F16
                              | ((uint32_t)(p.nbs >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbpp = p.nbpp, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs,
+    const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs,
                    nsub = p.nsub;
     const uint32_t b_lbo16 = (uint32_t)p.nbs, b_inc = 2 * b_lbo16;      // 16-byte units: K chunks of B are nbs columns apart
     const uint32_t b_sub = 2 * ksteps * b_lbo16, b2_sub = 2 * b_lbo16;   // sub-block strides of the B and B2 tiles
@@ -411,64 +443,59 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
     const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version = 1
-    const uint32_t a_lo0 = ((smem_u32(sm.ring) & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
-    const uint32_t b_lo0 = ((smem_u32(sm.btile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+    const uint32_t a_lo0 = ((sm.ring & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
+    const uint32_t b_lo0 = ((sm.btile & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
     const uint32_t a_inc = a_step * pitch16, a_wrap = ring_n * pitch16, a_end = a_lo0 + a_wrap;
-    const uint32_t a2_addr16 = (smem_u32(sm.a2ring) & 0x3FFFFu) >> 4, a2_wrap16 = (uint32_t)p.a2_groups * TC_G * (2048u >> 4);
+    // A2 rows: one 2 KB block of 128 x 16 B per box size; the fp16 MMA's two K chunks read the two blocks (one box
+    // size: both chunks read the same block, LBO = 0, and the second chunk of B2 is all zeros)
+    const uint32_t a2_slot16 = (uint32_t)p.a2_slot >> 4;
+    const uint32_t a2_lbo = (p.ncls == 2 ? (2048u >> 4) : 0u) << 16;
+    const uint32_t a2_addr16 = (sm.a2ring & 0x3FFFFu) >> 4, a2_wrap16 = (uint32_t)p.a2_groups * TC_G * a2_slot16;
     const uint32_t a2_end16 = a2_addr16 + a2_wrap16;
-    const uint32_t b2_lo = ((smem_u32(sm.b2tile) & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
+    const uint32_t b2_lo = ((sm.b2tile & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
     const bool corr = LEAN || p.dbg_acc == nullptr;
     const uint32_t a2_groups = p.a2_groups;
     const bool wrap = p.n_mirror == 0;       // no mirror slots: a row's K steps may run past the end of the ring
-    const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : 1u;
-    uint64_t *const a_full = sm.a_full, *const a_empty = sm.a_empty, *const a2_full = sm.a2_full, *const a2_empty = sm.a2_empty,
-                    *const t_full = sm.t_full, *const t_empty = sm.t_empty;
+    const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : leader;
+    const uint32_t f16_on = corr ? mma_on : 0u;
     volatile uint32_t *const prog_ = sm.prog;
-    mbar_wait(sm.bar_btile, 0, p.wd, 10 + mw, 0);
+    mbar_wait_addr(sm.bar_btile, 0, p.wd, 10, 0);
     TT_BEGIN();
-    // item-level state (both threads walk all items)
-    uint32_t o_item = 0;                     // global output-row index of the item's first row
-    uint32_t g_item = 0;                     // global page-row index of the item's first row
-    uint32_t a_item = a_lo0;                 // A descriptor (low word) of that row's ring slot
-    // own-row state
+    uint32_t o = 0;                          // global output-row index of the next row
+    uint32_t g = 0;                          // global page-row index of that row's first page row
+    uint32_t a_first = a_lo0;                // A descriptor (low word) of that page row's ring slot
+    uint32_t o_slot16 = a2_addr16;           // A2 ring slot address (>> 4) of that output row
     uint32_t rel_g = 0, rel_rows = TC_G;     // page-row groups: next to hand back / rows covered once it is
     uint32_t new_g = 0, new_par = 0, rows_ready = 0;
     uint32_t rel2_g = 0, rel2_rows = TC_G, new2_g = 0, new2_par = 0, rows2_ready = 0;
-    // accumulators of this pipeline: mw, mw+2, ...; job k of the pipeline uses number k mod nbpp
-    uint32_t kb = 0, kpar = 0;               // index of the next job's accumulator within the pipeline, its phase
+    uint32_t acc = 0, accpar = 0;            // the next job's accumulator and the phase of its barriers
     bool first_round = true;
-    uint32_t o_slot16 = a2_addr16 + mw * (2048u >> 4);   // A2 ring slot address (>> 4) of the next own row
     Item it;
     for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
         const uint32_t n_out_rows = it.ys1 - it.ys0;
-        const uint32_t j0 = (mw - o_item) & 1u;          // first own row of the item
-        uint32_t a_first = a_item + j0 * pitch16;        // (a_item < a_end, one slot more never needs two wraps)
-        if (a_first >= a_end) a_first -= a_wrap;
-        for (uint32_t j = j0; j < n_out_rows; j += 2) {
-            const uint32_t o = o_item + j, g_first = g_item + j;
-            TC_PROG(1 + mw, (1u << 24) | o);
-            // operands: page rows g_first .. g_first+n_hp-1 and the A2 row of this output
-            while (rows_ready < g_first + n_hp) {
-                TT(0, mbar_wait(a_full + new_g, new_par, p.wd, 12 + mw, o, sm.prog));
+        for (uint32_t j = 0; j < n_out_rows; j++) {
+            TC_PROG(1, (1u << 24) | o);
+            // operands: page rows g .. g+n_hp-1 and the A2 row of this output
+            while (rows_ready < g + n_hp) {
+                TT(0, mbar_wait_addr(sm.a_full + 8 * new_g, new_par, p.wd, 12, o, sm.prog));
                 rows_ready += TC_G;
                 if (++new_g == ring_g) new_g = 0, new_par ^= 1;
             }
             while (corr && rows2_ready <= o) {
-                TT(1, mbar_wait(a2_full + new2_g, new2_par, p.wd, 14 + mw, o, sm.prog));
+                TT(1, mbar_wait_addr(sm.a2_full + 8 * new2_g, new2_par, p.wd, 14, o, sm.prog));
                 rows2_ready += TC_G;
                 if (++new2_g == a2_groups) new2_g = 0, new2_par ^= 1;
             }
             // one job per sub-block: the row's operands are shared, the templates (B, B2) and the accumulator differ
             uint32_t b_lo = b_lo0, b2 = b2_lo;
-            for (uint32_t sb = 0; sb < (LEAN ? 1u : nsub); sb++, b_lo += b_sub, b2 += b2_sub) {
-                const uint32_t acc = mw + 2 * kb, d0 = acc * nbs;
-                TC_PROG(1 + mw, (2u << 24) | o);
-                if (!first_round) TT(2, mbar_wait<false>(t_empty + acc, kpar ^ 1, p.wd, 16 + mw, o, sm.prog));
+            for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub) {
+                const uint32_t d0 = acc * nbs;
+                TC_PROG(1, (2u << 24) | o);
+                if (!first_round) TT(2, mbar_wait_addr<false>(sm.t_empty + 8 * acc, accpar ^ 1, p.wd, 16, o, sm.prog));
                 tc_fence_after();
                 const long long ti_ = tron ? clock64() : 0;
-                // F = A2 . B2^T in fp32 (accumulate off).  K = 16 fp16 = two 16-byte chunks: both read the row's
-                // statistics (LBO = 0) and the second chunk of B2 is all zeros.
-                if (corr && mma_on) tc_mma_f16_overwrite(d0, desc_hi | o_slot16, desc_hi | b2, idesc16);
+                // F = A2 . B2^T in fp32 (accumulate off): K = 16 fp16 = two 16-byte chunks, one per box size
+                tc_mma_f16_overwrite_if(f16_on, d0, desc_hi | (o_slot16 | a2_lbo), desc_hi | b2, idesc16);
                 // K steps: consecutive ring slots (no wrap inside a row), consecutive B chunks
                 if (KS > 0) {
 #pragma unroll
@@ -484,38 +511,36 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
                     }
                 }
                 if (tron) tacc[3] += clock64() - ti_;
-                TT(4, tc_commit(t_full + acc));   // accumulator ready for the epilogue
-                if (++kb == nbpp) kb = 0, kpar ^= 1, first_round = false;
+                TT(4, tc_commit(leader, sm.t_full + 8 * acc));   // accumulator ready for the epilogue
+                if (++acc == nbuf) acc = 0, accpar ^= 1, first_round = false;
             }
-            // bookkeeping for the next own row (off the critical path: the tensor pipe is busy with this row)
-            o_slot16 += 2 * (2048u >> 4);
+            // bookkeeping for the next row (off the critical path: the tensor pipe is busy with this row)
+            o++;
+            g++;
+            o_slot16 += a2_slot16;
             if (o_slot16 >= a2_end16) o_slot16 -= a2_wrap16;
-            a_first += 2 * pitch16;
+            a_first += pitch16;
             if (a_first >= a_end) a_first -= a_wrap;
-            // hand back every group that lies entirely below what the next own output reads (at the end of an
-            // item that is the next item's first own row, whichever it is: use its first row)
-            const uint32_t g_next = j + 2 < n_out_rows ? g_first + 2 : g_item + n_out_rows + n_hp - 1;
-            const uint32_t o_next = j + 2 < n_out_rows ? o + 2 : o_item + n_out_rows;
-            while (rel_rows <= g_next) {
-                TT(4, tc_commit(a_empty + rel_g));
+            if (j + 1 == n_out_rows) {   // next item: its first row follows this item's last page row
+                g += n_hp - 1;
+                a_first += (n_hp - 1) * pitch16;
+                if (a_first >= a_end) a_first -= a_wrap;
+            }
+            // hand back every group that lies entirely below what the next output reads
+            while (rel_rows <= g) {
+                TT(4, tc_commit(leader, sm.a_empty + 8 * rel_g));
                 rel_rows += TC_G;
                 if (++rel_g == ring_g) rel_g = 0;
             }
-            while (rel2_rows <= o_next) {
-                TT(4, tc_commit(a2_empty + rel2_g));
+            while (rel2_rows <= o) {
+                TT(4, tc_commit(leader, sm.a2_empty + 8 * rel2_g));
                 rel2_rows += TC_G;
                 if (++rel2_g == a2_groups) rel2_g = 0;
             }
         }
-        // next item: its first row follows this item's last page row
-        o_item += n_out_rows;
-        g_item += n_out_rows + n_hp - 1;
-        a_item += ((n_out_rows + n_hp - 1) % ring_n) * pitch16;
-        if (a_item >= a_end) a_item -= a_wrap;
     }
-    TC_PROG(1 + mw, 9u << 24);
-    // groups this thread never passed explicitly (the other thread owned the last rows): nothing waits for them
-    if (mw == 0) TT_END(0);
+    TC_PROG(1, 9u << 24);
+    if (leader) TT_END(0);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
@@ -525,8 +550,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint8_t *btile = smem;
     uint8_t *ring = btile + ((p.btile_bytes + 127) & ~127u);
     uint8_t *raw = ring + (size_t)(p.ring + p.n_mirror) * p.row_pitch;  // + mirror slots: slot ring+i repeats slot i
-    uint8_t *a2ring = raw + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127);  // [TC_A2_GROUPS*4][128][16 B] fp16 x 8
-    uint8_t *b2tile = a2ring + (size_t)p.a2_groups * TC_G * 2048;         // [nsub][2][nbs][16 B]: chunk 0 constants, chunk 1 zeros
+    uint8_t *a2ring = raw + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127);  // [a2_groups*4][ncls][128][16 B] fp16 x 8
+    uint8_t *b2tile = a2ring + (size_t)p.a2_groups * TC_G * p.a2_slot;    // [nsub][2][nbs][16 B]: one K chunk per box size
     uint64_t *bars = (uint64_t *)(b2tile + (size_t)2 * p.nb * 16);   // b2tile: [nsub][2][nbs][16]
     uint64_t *bar_btile = bars;                       // 1
     uint64_t *raw_full = bars + 1;                    // TC_RAW_GROUPS
@@ -542,7 +567,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     if (threadIdx.x < 32) prog[threadIdx.x] = 0;
     volatile uint32_t *const prog_ = prog;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a broadcast: ptxas then knows it is warp-uniform, so the role branches are uniform branches and the
+    // issuing warp can keep its state in uniform registers (see tc_mma_role)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_btile, 1);
@@ -552,22 +579,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
             mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, 2);     // one tcgen05.commit per MMA-issuing thread
+            mbar_init(a_empty + i, 1);     // one tcgen05.commit of the MMA-issuing thread
         }
         for (int i = 0; i < TC_A2_GROUPS; i++) {
             mbar_init(a2_full + i, 4);     // one arrival per A2 warp
-            mbar_init(a2_empty + i, 2);
+            mbar_init(a2_empty + i, 1);
         }
         for (int i = 0; i < TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, TC_LISTS_PER_CTA / TC_TEAMS);  // one arrival per epilogue warp that reads the row
+            mbar_init(t_empty + i, TC_EPI_WARPS / 2);  // one arrival per epilogue warp of the team that drains the job
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // zero blocks and the B2 tile: B2[t] = {-b1, -b2, -b1, -a1, -a2, -a1, -BIG, 510 | -BIG} as fp16 hi/lo splits of
-    // b = s_n/n and a = thr*norm_n; +inf norm marks padding / constant templates (last entry -BIG: never a candidate)
+    // B2 tile: B2[t] = {-b1, -b2, -b1, -a1, -a2, -a1, -BIG, 510 | -BIG} as fp16 hi/lo splits of b = s_n/n and
+    // a = thr*norm_n, in the K chunk of the column's box size (the other chunk is zero); +inf norm marks padding /
+    // constant templates (last entry -BIG: never a candidate)
     for (int t = threadIdx.x; t < p.nb; t += TC_THREADS) {
-        const float2 c = p.colconst[t];
+        const float4 c = p.colconst[t];
         const bool pad = !(c.x < __int_as_float(0x7f800000));
         const float a = pad ? 0.f : p.thr * c.x, b = pad ? 0.f : c.y;
         const __half a1 = __float2half_rn(a), b1 = __float2half_rn(b);
@@ -578,9 +606,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const __half b2h = p.sshift ? __float2half_rn(16.f * __half2float(b2)) : b2;
         __align__(16) __half h[8] = {__hneg(b1h), __hneg(b2h), __hneg(b1), __hneg(a1), __hneg(a2), __hneg(a1), big, padh};
         const int sb = t / p.nbs, n = t - sb * p.nbs;      // layout [sub][K chunk][column][16 B]
+        const int chunk = (!pad && c.z != 0.f) ? 1 : 0;    // second box size -> second K chunk
         uint8_t *dst = b2tile + ((size_t)sb * 2 * p.nbs + n) * 16;
-        *(uint4 *)dst = *(const uint4 *)h;
-        *(uint4 *)(dst + (size_t)p.nbs * 16) = make_uint4(0, 0, 0, 0);
+        *(uint4 *)(dst + (size_t)chunk * p.nbs * 16) = *(const uint4 *)h;
+        *(uint4 *)(dst + (size_t)(1 - chunk) * p.nbs * 16) = make_uint4(0, 0, 0, 0);
     }
     if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
@@ -643,18 +672,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         if (in_group != 0 && elect_one()) mbar_arrive(raw_full + rg);  // the last, partial group
         if (lane == 0) TT_END(32);
-    } else if (warp == 1 || warp == 2) {
-        // ================================================================== MMA issuers (tc_mma_role)
-        if (elect_one()) {
-            TcSmem sm = {btile, ring, a2ring, b2tile, bar_btile, a_full, a_empty, a2_full, a2_empty, t_full, t_empty, prog};
-            const uint32_t mw = warp - 1;
-            const bool lean = p.nsub == 1 && p.dbg_acc == nullptr;
-            switch (p.n_mirror && lean ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
-                case 6: tc_mma_role<6, true>(p, sm, mw); break;
-                case 7: tc_mma_role<7, true>(p, sm, mw); break;
-                case 8: tc_mma_role<8, true>(p, sm, mw); break;
-                default: tc_mma_role<0, false>(p, sm, mw); break;
-            }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer (tc_mma_role): the whole warp, converged
+        const uint32_t sbase = smem_u32(smem);
+        const TcSmem sm = {sbase + (uint32_t)(btile - smem), sbase + (uint32_t)(ring - smem), sbase + (uint32_t)(a2ring - smem),
+                           sbase + (uint32_t)(b2tile - smem), sbase + (uint32_t)((uint8_t *)bar_btile - smem),
+                           sbase + (uint32_t)((uint8_t *)a_full - smem), sbase + (uint32_t)((uint8_t *)a_empty - smem),
+                           sbase + (uint32_t)((uint8_t *)a2_full - smem), sbase + (uint32_t)((uint8_t *)a2_empty - smem),
+                           sbase + (uint32_t)((uint8_t *)t_full - smem), sbase + (uint32_t)((uint8_t *)t_empty - smem), prog};
+        const uint32_t leader = elect_flag();
+        switch (p.n_mirror && p.dbg_acc == nullptr ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
+            case 6: tc_mma_role<6, true>(p, sm, leader); break;
+            case 7: tc_mma_role<7, true>(p, sm, leader); break;
+            case 8: tc_mma_role<8, true>(p, sm, leader); break;
+            default: tc_mma_role<0, false>(p, sm, leader); break;
         }
         __syncwarp();
     }
@@ -705,7 +736,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     } else if (warp < 12) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_A2));
         // ================================================================== A2 rows: window statistics -> fp16 operand
-        // One warp per output row, four rows per handshake.  For window m of output row y:
+        // One warp per output row, four rows per handshake.  For window m of output row y and each box size:
         //   A2 = {S_hi, S_hi, S_lo, P_1, P_1, P_2, V, 2^15}   (S = s_p split at bit 6; P = norm_p split hi/lo)
         // V = BIG when the window can never hit: x outside [1, r_w-n_w] (ncc.rs:281) or a constant window
         // (norm_p = +inf marker: rnorm_p = inf in the reference, ncc.cpp:216-220).  V = -BIG (always a
@@ -732,34 +763,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                     have = get_item(p, cur_idx, it);
                 }
                 const int y = it.ys0 + (int)(o - item_o0);
-                uint8_t *dst = a2ring + (size_t)(ag * TC_G + w) * 2048;
                 const size_t rowoff = (size_t)it.page * p.plane_page_stride + (size_t)y * p.spitch + it.x0;
-                uint32_t sv[4];
-                float pv[4];
+                for (int c = 0; c < p.ncls; c++) {
+                    uint8_t *dst = a2ring + (size_t)(ag * TC_G + w) * p.a2_slot + c * 2048;
+                    const uint32_t *spc = p.sp[c];
+                    const float *pfc = p.pf[c];
+                    const int x_last = p.r_w - (c ? p.n_w2 : p.n_w);
+                    const float bmax = p.bmax[c], amax = p.amax[c];
+                    uint32_t sv[4];
+                    float pv[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int m = lane + 32 * i, gx = it.x0 + m;
-                    const bool ok = gx >= 1 && gx <= p.r_w - p.n_w && !(TC_EXP && (p.dbg_mode & 8));
-                    sv[i] = ok ? __ldg(p.sp + rowoff + m) : 0u;
-                    pv[i] = ok ? __ldg(p.pf + rowoff + m) : __int_as_float(0x7f800000);
-                }
+                    for (int i = 0; i < 4; i++) {
+                        const int m = lane + 32 * i, gx = it.x0 + m;
+                        const bool ok = gx >= 1 && gx <= x_last && !(TC_EXP && (p.dbg_mode & 8));
+                        sv[i] = ok ? __ldg(spc + rowoff + m) : 0u;
+                        pv[i] = ok ? __ldg(pfc + rowoff + m) : __int_as_float(0x7f800000);
+                    }
 #pragma unroll
-                for (int i = 0; i < 4 && !(TC_EXP && (p.dbg_mode & 32)); i++) {
-                    const int m = lane + 32 * i;
-                    const bool valid = pv[i] < __int_as_float(0x7f800000);
-                    const bool lin = valid && (p.bmax * (float)sv[i] + p.amax * pv[i] <= TC_KCAP);
-                    const uint32_t s = lin ? sv[i] : 0u;
-                    const float P = lin ? pv[i] : 0.f;
-                    // S = S_hi + S_lo, both exact in fp16: split at bit 6 (S < 2^16), or at bit 10 with S_hi stored /16 for
-                    // boxes of more than 256 pixels (S < 2^19); the factor 16 is in B2
-                    const float s_hi = p.sshift ? (float)((s & ~1023u) >> 4) : (float)(s & ~63u);
-                    const float s_lo = p.sshift ? (float)(s & 1023u) : (float)(s & 63u);
-                    const __half p1 = __float2half_rn(P);
-                    const __half p2 = __float2half_rn(P - __half2float(p1));
-                    const __half shi = __float2half_rn(s_hi), slo = __float2half_rn(s_lo);
-                    const __half v = __float2half_rn(valid ? (lin ? 0.f : -TC_BIG) : TC_BIG), k = __float2half_rn(32768.f);
-                    __align__(16) __half h[8] = {shi, shi, slo, p1, p1, p2, v, k};
-                    *(uint4 *)(dst + m * 16) = *(const uint4 *)h;
+                    for (int i = 0; i < 4 && !(TC_EXP && (p.dbg_mode & 32)); i++) {
+                        const int m = lane + 32 * i;
+                        const bool valid = pv[i] < __int_as_float(0x7f800000);
+                        const bool lin = valid && (bmax * (float)sv[i] + amax * pv[i] <= TC_KCAP);
+                        const uint32_t s = lin ? sv[i] : 0u;
+                        const float P = lin ? pv[i] : 0.f;
+                        // S = S_hi + S_lo, both exact in fp16: split at bit 6 (S < 2^16), or at bit 10 with S_hi stored /16 for
+                        // boxes of more than 256 pixels (S < 2^19); the factor 16 is in B2
+                        const float s_hi = p.sshift ? (float)((s & ~1023u) >> 4) : (float)(s & ~63u);
+                        const float s_lo = p.sshift ? (float)(s & 1023u) : (float)(s & 63u);
+                        const __half p1 = __float2half_rn(P);
+                        const __half p2 = __float2half_rn(P - __half2float(p1));
+                        const __half shi = __float2half_rn(s_hi), slo = __float2half_rn(s_lo);
+                        const __half v = __float2half_rn(valid ? (lin ? 0.f : -TC_BIG) : TC_BIG), k = __float2half_rn(32768.f);
+                        __align__(16) __half h[8] = {shi, shi, slo, p1, p1, p2, v, k};
+                        *(uint4 *)(dst + m * 16) = *(const uint4 *)h;
+                    }
                 }
             }
             fence_proxy_async();
@@ -772,105 +809,118 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
         // ================================================================== epilogue (16 warps = 2 teams x 4 lane quarters x 2)
         // The accumulator holds the bits of fp32 C0 + d: one 3-input max per column pair (a tree, so the
-        // FMNMX3s are independent), one vote per 32 columns.  Output rows alternate between two TEAMS of 8
-        // warps, so a warp pays the per-row overhead (barrier wait, fences, arrive) only every second row;
-        // inside a team the two warps of a lane quarter take the even / odd 32-column units.  Two units are
-        // in registers at a time; the accumulator goes back to the MMA thread as soon as the warp's LAST unit
-        // has landed, before it is screened.
+        // FMNMX3s are independent), one vote per 32 columns.  Jobs alternate between two TEAMS of 8 warps, so a
+        // warp pays the per-job overhead (barrier wait, fences, arrive) only every second job; inside a team the two
+        // warps of a lane quarter take one half of the job's columns each, as chunks of 32 (+ one of 16).  Two chunks
+        // are in registers at a time; the accumulator goes back to the MMA warp as soon as the warp's LAST chunk has
+        // landed, before it is screened.
         const int e = warp - 12;
         const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
-        const int team = (e >> 2) & 1, sub = e >> 3;   // team = which rows, sub = which units of a row (sub, sub+2, ...)
-        constexpr int USTEP = 2;
+        const int team = (e >> 2) & 1, half = e >> 3;   // team = which jobs, half = which half of a job's columns
         const int m = q * 32 + lane;              // window within the strip
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint32_t nbpp = p.nbpp, nsub = p.nsub;
-        const int nunits = p.nunits;
+        const uint32_t nbuf = p.nbuf, nsub = p.nsub;
+        const int cols_w = p.nbs >> 1;            // columns per warp (a multiple of 16)
+        const int n32 = cols_w >> 5, nch = n32 + ((cols_w >> 4) & 1);   // full chunks, chunks incl. the 16-column tail (<= 4)
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * cols_w);
         const float T = p.dbg_acc ? 3.0e38f : TC_C0 - TC_MARGIN;
-        uint32_t kb = 0, kpar = 0;                // the team's next job: accumulator team + 2*kb, phase kpar (as in tc_mma_role)
+        uint32_t acc = 0, accpar = 0;             // the next job's accumulator and phase (as in tc_mma_role)
+        uint32_t job = 0;
         Hit *my_list = p.cands + (size_t)(blockIdx.x * TC_LISTS_PER_CTA + e) * p.cand_cap;
         uint32_t my_count = 0;
-        uint32_t orow0 = 0;                       // global output-row index of the current item's first row
         const bool no_ld = TC_EXP && (p.dbg_mode & 1), no_screen = TC_EXP && (p.dbg_mode & 2);
         const int dbg_sub = p.dbg_acc ? p.dbg_col / p.nbs : -1, dbg_c = p.dbg_acc ? p.dbg_col % p.nbs : 0;
+        const bool h0 = !no_ld, h1 = nch > 1 && !no_ld, h2 = nch > 2 && !no_ld, h3 = nch > 3 && !no_ld;
         TT_BEGIN();
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
             const int gx = it.x0 + m;
-            for (int y = it.ys0 + (int)((team - orow0) & 1u); y < it.ys1; y += 2) {   // the team's rows of this item
-              for (uint32_t sb = 0; sb < nsub; sb++) {
-                const uint32_t acc = team + 2 * kb;
-                if (lane == 0) TC_PROG(warp, (uint32_t)(y - it.ys0) + orow0);
+            for (int y = it.ys0; y < it.ys1; y++) {
+              for (uint32_t sb = 0; sb < nsub; sb++, job++) {
+                if ((job & 1u) == (uint32_t)team) {
+                if (lane == 0) TC_PROG(warp, job);
                 // ONE warp of the team polls the mbarrier (polling costs shared-memory bandwidth, which the tensor core's
                 // operand reads already use to ~80 %); its team-mates wait on a hardware named barrier
-                if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, kpar, p.wd, 20 + team, y, prog));
+                if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, accpar, p.wd, 20 + team, y, prog));
                 asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
                 tc_fence_after();
                 const long long tseen_ = tron ? clock64() : 0;
                 const uint32_t tb = tlane + acc * p.nbs;
-                const uint32_t cbase = p.col_base + sb * p.nbs;
+                const uint32_t cbase = p.col_base + sb * p.nbs + half * cols_w;
                 auto release = [&]() {  // every tcgen05.ld of this job has completed: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty + acc);
                     if (tron) tacc[3] += clock64() - tseen_;   // time from "accumulator full" seen to "accumulator released"
                 };
-                auto screen = [&](uint32_t (&v)[32], int u) {
-                    float t[11];
+                auto ld = [&](uint32_t (&v)[32], int c) {   // chunk c: 32 columns, or the 16-column tail
+                    if (c < n32) tc_ld32(tb + c * 32, v);
+                    else tc_ld16(tb + c * 32, v);
+                };
+                auto screen = [&](uint32_t (&v)[32], int c) {
+                    const bool full = c < n32;
+                    float t[6];
 #pragma unroll
-                    for (int j = 0; j < 10; j++)
+                    for (int j = 0; j < 5; j++)
                         asm("max.f32 %0, %1, %2, %3;"
                             : "=f"(t[j])
                             : "f"(__uint_as_float(v[3 * j])), "f"(__uint_as_float(v[3 * j + 1])), "f"(__uint_as_float(v[3 * j + 2])));
-                    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
-                    float a, b, c, mx;
+                    t[5] = __uint_as_float(v[15]);
+                    float a, b, mx;
                     asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(t[0]), "f"(t[1]), "f"(t[2]));
                     asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(t[3]), "f"(t[4]), "f"(t[5]));
-                    asm("max.f32 %0, %1, %2, %3;" : "=f"(c) : "f"(t[6]), "f"(t[7]), "f"(t[8]));
-                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(t[9]), "f"(t[10]), "f"(a));
-                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(b), "f"(c));
+                    mx = fmaxf(a, b);
+                    if (full) {   // warp-uniform
+                        float u[6];
+#pragma unroll
+                        for (int j = 0; j < 5; j++)
+                            asm("max.f32 %0, %1, %2, %3;"
+                                : "=f"(u[j])
+                                : "f"(__uint_as_float(v[16 + 3 * j])), "f"(__uint_as_float(v[17 + 3 * j])), "f"(__uint_as_float(v[18 + 3 * j])));
+                        u[5] = __uint_as_float(v[31]);
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(u[0]), "f"(u[1]), "f"(u[2]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(u[3]), "f"(u[4]), "f"(u[5]));
+                        asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(a), "f"(b));
+                    }
                     if (__any_sync(0xffffffffu, mx >= T)) {
-                        // rare: some lane of the warp has a survivor among these 32 columns
+                        // rare: some lane of the warp has a survivor among these columns
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= T ? 1u : 0u) << j;
-                        append_candidates(my_list, p.cand_cap, my_count, mask, cbase + u * 32, it.page, gx, y);
+                        if (!full) mask &= 0xFFFFu;
+                        append_candidates(my_list, p.cand_cap, my_count, mask, cbase + c * 32, it.page, gx, y);
                     }
                 };
-                if (p.dbg_acc && sub == 0 && (int)sb == dbg_sub) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
-                    const uint32_t a = tc_ld1(tb + dbg_c);
+                if (p.dbg_acc && half == 0 && (int)sb == dbg_sub) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
+                    const uint32_t a = tc_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.nbs + dbg_c);
                     tc_wait_ld();
-                    if (gx >= 1 && gx <= p.r_w - p.n_w) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
+                    if (gx >= 1 && gx <= p.dbg_xlast) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
                 }
-                // this warp's units: sub, sub + USTEP, ... (nunits <= 8), two at a time
-                const int u0 = sub, u1 = sub + USTEP, u2 = sub + 2 * USTEP, u3 = sub + 3 * USTEP;
-                const bool h0 = u0 < nunits && !no_ld, h1 = u1 < nunits && !no_ld, h2 = u2 < nunits && !no_ld,
-                           h3 = u3 < nunits && !no_ld;
                 uint32_t va[32], vb[32];
-                if (h0) tc_ld32(tb + u0 * 32, va);
-                if (h1) tc_ld32(tb + u1 * 32, vb);
+                if (h0) ld(va, 0);
+                if (h1) ld(vb, 1);
                 if (h0) tc_wait_ld32(va);
                 if (h1) tc_wait_ld32(vb);
-                // a warp with more than two units screens its first two while the next two are in flight; the last
+                // a warp with more than two chunks screens its first two while the next two are in flight; the last
                 // (or only) pair is screened after the accumulator has been released.  One common tail for both cases
-                // keeps the code small (the single-warp roles are instruction-cache sensitive).
+                // keeps the code small.
                 if (h2) {
-                    if (!no_screen) screen(va, u0);
-                    tc_ld32(tb + u2 * 32, va);
-                    if (!no_screen) screen(vb, u1);
-                    if (h3) tc_ld32(tb + u3 * 32, vb);
+                    if (!no_screen) screen(va, 0);
+                    ld(va, 2);
+                    if (!no_screen) screen(vb, 1);
+                    if (h3) ld(vb, 3);
                     tc_wait_ld32(va);
                     if (h3) tc_wait_ld32(vb);
                 }
                 release();
                 if (!no_screen) {
-                    if (h2 || h0) screen(va, h2 ? u2 : u0);
-                    if (h2 ? h3 : h1) screen(vb, h2 ? u3 : u1);
+                    if (h2 || h0) screen(va, h2 ? 2 : 0);
+                    if (h2 ? h3 : h1) screen(vb, h2 ? 3 : 1);
                 }
                 if (tron) tacc[4] += clock64() - tseen_;       // ... to the end of the job (screens, candidates)
-                if (++kb == nbpp) kb = 0, kpar ^= 1;
+                }
+                if (++acc == nbuf) acc = 0, accpar ^= 1;
               }
             }
-            orow0 += it.ys1 - it.ys0;
         }
         if (lane == 0) p.cand_count[blockIdx.x * TC_LISTS_PER_CTA + e] = my_count;
         if (e == 0 && lane == 0) TT_END(8);
@@ -896,17 +946,18 @@ struct CandArgs {
     uint32_t cand_cap, n_lists;
     const unsigned int *cand_count;  // [n_lists]
     unsigned int *cand_max;  // high-water mark of a list's count (overflow detection on the host)
-    const uint32_t *tpl_of;  // [n_blocks*nb] bank index per class column (0xFFFFFFFF = padding)
+    const uint32_t *tpl_of;  // [n_blocks*nb] bank index per group column (0xFFFFFFFF = padding)
     const uint32_t *cls_of;  // [n_blocks*nb] index of the column's template within `rows`
-    const uint8_t *rows;     // [n_tpl][n_h][np] zero-padded template rows of the class
+    const uint8_t *rows;     // [n_tpl][n_h][np] zero-padded template rows of the group
     const TplInfo *tpl;
     const uint8_t *inv;
     size_t inv_page_stride;
-    int pitch, n_w, n_h, np;
-    const uint32_t *sp;
+    int pitch, n_h, np;
+    int n_w[2];              // box widths of the group (one or two box sizes of the same height)
+    const uint32_t *sp[2];   // window-sum planes per box size
     int spitch;
     size_t plane_page_stride;
-    double n_d, thr_d;
+    double n_d[2], thr_d;
     HitSink sink;
 };
 
@@ -932,8 +983,10 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             // tcgen05 path does not materialise an s2p plane (4 B per window of HBM traffic saved in window_stats)
             // (issued first: the statistics and the template record are random 4..32-byte reads whose latency then overlaps the rows)
             const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
-            const uint32_t s_p = __ldg(a.sp + o);
             const TplInfo ti = a.tpl[t];
+            const int bs = (int)ti.n_w == a.n_w[0] ? 0 : 1;   // which box size of the group
+            const uint32_t s_p = __ldg(a.sp[bs] + o);
+            const int n_w = a.n_w[bs];
             uint32_t acc = 0, s2_p = 0;
             const int pitch4 = a.pitch >> 2;
             auto rows = [&](auto nw4_c) {   // nw4_c: words per template row as a compile-time constant (0: run-time nw4)
@@ -952,7 +1005,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
                             const uint32_t hi = __ldg(prow + q + 1);
                             const uint32_t w = __funnelshift_r(lo, hi, sh);
                             acc = __dp4a(w, tw[k], acc);
-                            const int valid = a.n_w - 4 * q;   // bytes of this word inside the window
+                            const int valid = n_w - 4 * q;   // bytes of this word inside the window
                             const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
                             s2_p = __dp4a(wm, wm, s2_p);
                             lo = hi;
@@ -963,7 +1016,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             if (nw4 == 4) rows(std::integral_constant<int, 4>{});
             else if (nw4 == 8) rows(std::integral_constant<int, 8>{});
             else rows(std::integral_constant<int, 0>{});
-            const double rn_p = patch_rnorm(s_p, s2_p, a.n_d);
+            const double rn_p = patch_rnorm(s_p, s2_p, a.n_d[bs]);
             float sim;
             if (ncc_exact(acc, s_p, rn_p, ti.s_n, ti.n_recip, ti.rnorm_n, a.thr_d, &sim)) {
                 auto g = cg::coalesced_threads();
@@ -986,21 +1039,26 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_mirror, int row_pitch, int nb, int a2_groups)
+static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_mirror, int row_pitch, int nb, int a2_groups, int a2_slot)
 {
     return ((btile_bytes + 127) & ~127u) + (size_t)(ring + n_mirror) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
-           (size_t)a2_groups * TC_G * 2048 + (size_t)2 * nb * 16 +
+           (size_t)a2_groups * TC_G * a2_slot + (size_t)2 * nb * 16 +
            (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 2 * TC_MAX_BUF) * 8 + 64 + 128;
 }
 
-int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t n_h, uint32_t np, uint32_t n_tpl,
-                   const uint32_t *bank_index, const TplInfo *info)
+int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n_h, uint32_t np)
 {
     tc.supported = false;
-    tc.n_w = n_w;
+    if (ncls < 1 || ncls > 2) return 0;
+    tc.ncls = ncls;
+    tc.n_w = src[0].n_w;
+    tc.n_w2 = ncls == 2 ? src[1].n_w : 0;
     tc.n_h = n_h;
     tc.np = np;
+    tc.n_tpl0 = src[0].n_tpl;
+    const uint32_t n_tpl = src[0].n_tpl + (ncls == 2 ? src[1].n_tpl : 0);
     tc.n_tpl = n_tpl;
+    const uint32_t n_w_max = std::max(tc.n_w, tc.n_w2);
     const uint32_t n_hp = np == 16 ? (n_h + 1) & ~1u : n_h;
     tc.kchunks = n_h * (np / 16);
     tc.ksteps = (tc.kchunks + 1) / 2;
@@ -1008,76 +1066,86 @@ int tc_class_build(TcClass &tc, const uint8_t *rows_host, uint32_t n_w, uint32_t
     // one ring slot per K step, so the issue loop can wrap and the mirror slots are not needed
     const bool tall = n_hp > 16;
     tc.look_groups = tall ? 1 : TC_LOOK_GROUPS;
-    tc.a2_groups = tall ? 2 : TC_A2_GROUPS;
     tc.n_mirror = np == 16 ? n_hp - 1 : 0;
     tc.ring_groups = (n_hp + TC_G - 1 + TC_G - 1) / TC_G + tc.look_groups;
     const int ring = tc.ring_groups * TC_G;
     const int row_pitch = np == 16 ? 2048 : 2304;
+    const int a2_slot = 2048 * (int)ncls;
     if (tc.ring_groups > (uint32_t)TC_RING_MAX) return 0;  // unsupported shape -> SIMT kernel
     // Boxes of more than 256 pixels: b*S + a*P outgrows the 23-bit linear range of the fp32 trick, so the SCREEN runs at
     // 1/2^sshift scale: the B tile holds ceil(t / 2^sshift) (acc' >= acc / 2^sshift: still errs towards more
     // candidates), b and a are divided by 2^sshift; the exact pass uses the true templates.
     tc.sshift = 0;
-    while ((n_w * n_h) > (256u << tc.sshift)) tc.sshift++;
+    while ((n_w_max * n_h) > (256u << tc.sshift)) tc.sshift++;
     if (tc.sshift > 3) return 0;
-    // largest column count per launch (multiple of 32, <= 256) whose B tiles fit next to the rings
-    int nb_max = 256;
+    // A2 ring: 4 groups of 4 rows when they fit next to a useful B tile, else 2 (tall boxes, two box sizes)
+    tc.a2_groups = (tall || ncls == 2) ? 2 : TC_A2_GROUPS;
+    // largest column count per launch (multiple of 32, <= 512 = two sub-blocks of 256) whose B tiles fit next to the rings
+    int nb_max = 512;
     while (nb_max >= 32 &&
-           tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)tc.n_mirror, row_pitch, nb_max, (int)tc.a2_groups) > TC_SMEM_BUDGET)
+           tc_smem_bytes(2 * tc.ksteps * nb_max * 16, ring, (int)tc.n_mirror, row_pitch, nb_max, (int)tc.a2_groups, a2_slot) > TC_SMEM_BUDGET)
         nb_max -= 32;
     if (nb_max < 32) return 0;
+    // Column blocks (launches) and sub-blocks (jobs per output row).  A sub-block is one accumulator: <= 256 columns, a
+    // multiple of 32 (the epilogue works in 32-column units and every column of a unit must be written by the MMA; padding
+    // columns carry -BIG in B2 and can never survive the screen).  More than 256 columns per launch are two sub-blocks that
+    // share the row's operands; the accumulators then form a ring of 512 / columns-per-sub-block entries.
+    // FOCR_TC_NBMAX / FOCR_TC_SPLIT: experiments (cap the columns per launch / always two sub-blocks).
+    if (const char *e = getenv("FOCR_TC_NBMAX")) nb_max = std::max(32, std::min(nb_max, atoi(e) & ~31));
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
     const uint32_t per_blk = (n_tpl + tc.n_blocks - 1) / tc.n_blocks;   // templates per launch
-    // Sub-blocks: a launch may split its columns into accumulator-sized groups that share the row's operands (one job per
-    // group and row), which gives each issuing thread / epilogue team two accumulators even for wide banks.  Measured
-    // (B200, 222 templates): 2 x 128 columns is SLOWER than 1 x 224 (0.465 vs 0.417 ms/page) -- the cost of a job is set by
-    // the control threads' instruction streams, not by the MMAs -- so the split is only taken on request
-    // (FOCR_TC_SPLIT=1, experiments).  Column counts are multiples of 32: the epilogue works in 32-column units and every
-    // column of a unit must be written by the MMA (padding columns carry -BIG in B2 and can never survive the screen).
-    tc.nsub = (per_blk > 128 && getenv("FOCR_TC_SPLIT")) ? 2 : 1;
+    tc.nsub = (per_blk > 256 || (per_blk > 64 && getenv("FOCR_TC_SPLIT"))) ? 2 : 1;
     const uint32_t per_sub = (per_blk + tc.nsub - 1) / tc.nsub;
     tc.nbsub = (per_sub + 31) & ~31u;
     tc.nb = tc.nsub * tc.nbsub;
     const size_t subtile = (size_t)2 * tc.ksteps * tc.nbsub * 16, tile = subtile * tc.nsub;
     std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
-    std::vector<float2> cst((size_t)tc.n_blocks * tc.nb);
+    std::vector<float4> cst((size_t)tc.n_blocks * tc.nb);
     std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu), cof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
+    std::vector<uint8_t> rows_all((size_t)n_tpl * n_h * np);
     const float inf = INFINITY;
-    for (auto &c : cst) c = make_float2(inf, 0.f);
-    tc.blk_bmax.assign(tc.n_blocks, 0.f);
-    tc.blk_normmax.assign(tc.n_blocks, 0.f);
+    for (auto &c : cst) c = make_float4(inf, 0.f, 0.f, 0.f);
+    for (int c = 0; c < 2; c++) {
+        tc.blk_bmax[c].assign(tc.n_blocks, 0.f);
+        tc.blk_normmax[c].assign(tc.n_blocks, 0.f);
+    }
     tc.col_of.assign(n_tpl, 0);
     for (uint32_t i = 0; i < n_tpl; i++) {
+        const uint32_t bs = i < tc.n_tpl0 ? 0 : 1, li = bs ? i - tc.n_tpl0 : i;   // box size, index within it
+        const uint8_t *trows = src[bs].rows_host + (size_t)li * n_h * np;
+        memcpy(&rows_all[(size_t)i * n_h * np], trows, (size_t)n_h * np);
         const uint32_t blk = i / per_blk, r = i % per_blk, sub = r / per_sub, n = r % per_sub;
         const uint32_t col = sub * tc.nbsub + n;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
             const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
             uint8_t *dst = &bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16];
-            const uint8_t *src = rows_host + ((size_t)i * n_h + row) * np + boff;
-            for (int q = 0; q < 16; q++) dst[q] = (uint8_t)((src[q] + (1u << tc.sshift) - 1u) >> tc.sshift);
+            const uint8_t *sp = trows + (size_t)row * np + boff;
+            for (int q = 0; q < 16; q++) dst[q] = (uint8_t)((sp[q] + (1u << tc.sshift) - 1u) >> tc.sshift);
         }
-        const TplInfo &ti = info[i];
+        const TplInfo &ti = src[bs].info[li];
         // norm_n = sqrt(s2_n - s_n^2/n) = 1/rnorm_n ; constant (incl. all-zero) templates can never hit
         const double scale = 1.0 / (double)(1u << tc.sshift);
         const double norm_n = scale / ti.rnorm_n, b_t = scale * ti.s_n * ti.n_recip;
         const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
-        cst[(size_t)blk * tc.nb + col] = make_float2(ok ? (float)norm_n : inf, (float)b_t);
-        tof[(size_t)blk * tc.nb + col] = bank_index[i];
+        cst[(size_t)blk * tc.nb + col] = make_float4(ok ? (float)norm_n : inf, (float)b_t, (float)bs, 0.f);
+        tof[(size_t)blk * tc.nb + col] = src[bs].bank_index[li];
         cof[(size_t)blk * tc.nb + col] = i;
         tc.col_of[i] = blk * tc.nb + col;
         if (ok) {
-            tc.blk_bmax[blk] = std::max(tc.blk_bmax[blk], (float)b_t);
-            tc.blk_normmax[blk] = std::max(tc.blk_normmax[blk], (float)norm_n);
+            tc.blk_bmax[bs][blk] = std::max(tc.blk_bmax[bs][blk], (float)b_t);
+            tc.blk_normmax[bs][blk] = std::max(tc.blk_normmax[bs][blk], (float)norm_n);
         }
     }
     if (cudaMalloc(&tc.cls_of, cof.size() * 4) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.cls_of, cof.data(), cof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.b_tiles, bt.size()) != cudaSuccess) return -1;
-    if (cudaMalloc(&tc.consts, cst.size() * sizeof(float2)) != cudaSuccess) return -1;
+    if (cudaMalloc(&tc.consts, cst.size() * sizeof(float4)) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.tpl_of, tof.size() * 4) != cudaSuccess) return -1;
+    if (cudaMalloc(&tc.rows, rows_all.size()) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.b_tiles, bt.data(), bt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
-    if (cudaMemcpy(tc.consts, cst.data(), cst.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.consts, cst.data(), cst.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.tpl_of, tof.data(), tof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.rows, rows_all.data(), rows_all.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     tc.supported = true;
     return 0;
 }
@@ -1088,10 +1156,12 @@ void tc_class_release(TcClass &tc)
     if (tc.consts) cudaFree(tc.consts);
     if (tc.tpl_of) cudaFree(tc.tpl_of);
     if (tc.cls_of) cudaFree(tc.cls_of);
+    if (tc.rows) cudaFree(tc.rows);
     tc.cls_of = nullptr;
     tc.b_tiles = nullptr;
     tc.consts = nullptr;
     tc.tpl_of = nullptr;
+    tc.rows = nullptr;
     tc.supported = false;
 }
 
@@ -1110,6 +1180,8 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.r_w = a.r_w;
     p.r_h = a.r_h;
     p.n_w = tc.n_w;
+    p.n_w2 = tc.n_w2;
+    p.ncls = tc.ncls;
     p.n_h = tc.n_h;
     p.np = tc.np;
     p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
@@ -1118,14 +1190,12 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.nsub = tc.nsub;
     p.nbs = tc.nbsub;
     p.nunits = tc.nbsub / 32;
-    // An EVEN number of accumulators: with two issuing threads / two epilogue teams on alternate rows, accumulator b is then
-    // always written by thread b%2 and read by team b%2, so each of them sees every phase of its barriers.  (With an odd
-    // count the owners alternate, a waiter can fall two phases behind and the parity test aliases.)
-    p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF) & ~1;
-    p.nbpp = p.nbuf / 2;
+    p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
+    if (const char *e = getenv("FOCR_TC_NBUF")) p.nbuf = std::max(1, std::min(p.nbuf, atoi(e)));   // experiments
     p.ring_groups = tc.ring_groups;   // rows y..y+n_hp-1 may straddle one more group; + look-ahead
     p.n_mirror = tc.n_mirror;
     p.a2_groups = tc.a2_groups;
+    p.a2_slot = 2048 * (int)tc.ncls;
     p.sshift = tc.sshift;
     p.ring = p.ring_groups * TC_G;
     p.row_pitch = tc.np == 16 ? 2048 : 2304;
@@ -1134,8 +1204,11 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     // the screen only has to pass a SUPERSET of the hits: |sim| <= 1 up to rounding, so thresholds beyond +-2 are
     // clamped (keeps thr*norm_n inside the fp16 range); cand_exact_kernel applies the real threshold
     p.thr = (float)std::min(std::max(a.thr_d, -2.0), 2.0);
-    p.sp = a.sp;
-    p.pf = a.pf;
+    p.sp[0] = a.sp;
+    p.pf[0] = a.pf;
+    p.sp[1] = tc.ncls == 2 ? a.sp2 : a.sp;
+    p.pf[1] = tc.ncls == 2 ? a.pf2 : a.pf;
+    if (tc.ncls == 2 && (!a.sp2 || !a.pf2)) return cudaErrorInvalidValue;
     p.spitch = a.spitch;
     p.plane_page_stride = a.plane_page_stride;
     p.cands = a.cands;
@@ -1143,18 +1216,33 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.cand_count = a.cand_count;
     p.wd = a.cand_max ? a.cand_max + 1 : nullptr;   // api.cu: flags[4..9] follow the candidate high-water mark
     p.n_pages = n_pages;
-    const int xs = a.r_w - (int)tc.n_w + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
+    // windows of the NARROWEST box size: the strips cover x = 1 .. r_w - min n_w (the wider box flags its last columns invalid)
+    const int n_w_min = tc.ncls == 2 ? (int)std::min(tc.n_w, tc.n_w2) : (int)tc.n_w;
+    const int xs = a.r_w - n_w_min + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
     if (xs <= 0 || ys <= 0) return cudaSuccess;
     p.n_xstrips = (xs + 127) / 128;
-    p.n_ysegs = (ys + TC_YSEG - 1) / TC_YSEG;
-    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_mirror, p.row_pitch, p.nb, p.a2_groups);
+    // Work items = (page, 128-window strip, y-segment), dealt round-robin to one persistent CTA per SM.  Segments of 128
+    // rows amortise the n_hp-1 extra page rows an item expands; a batch that would leave SMs idle or unbalanced (a single
+    // 608x800 page: 5 strips x 7 segments for 148 SMs) takes as many shorter segments as fill its last wave.
+    {
+        const long long cols = (long long)n_pages * p.n_xstrips;
+        const long long segs_min = (ys + TC_YSEG - 1) / TC_YSEG;
+        const long long waves = (cols * segs_min + sm_count - 1) / sm_count;
+        long long segs = segs_min;
+        if (waves < 8) segs = std::max(segs_min, std::min<long long>(waves * sm_count / cols, (ys + 7) / 8));
+        p.yseg = (int)((ys + segs - 1) / segs);
+    }
+    if (const char *e = getenv("FOCR_TC_YSEG")) p.yseg = std::max(1, atoi(e));   // experiments
+    p.n_ysegs = (ys + p.yseg - 1) / p.yseg;
+    const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_mirror, p.row_pitch, p.nb, p.a2_groups, p.a2_slot);
     cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int items = n_pages * p.n_xstrips * p.n_ysegs;
     const int grid = std::min(items, sm_count);
     p.dbg_acc = dbg_acc;
-    const uint32_t dbg_colidx = dbg_acc ? tc.col_of[dbg_pos] : 0;   // dbg_pos = template index within the class
+    const uint32_t dbg_colidx = dbg_acc ? tc.col_of[dbg_pos] : 0;   // dbg_pos = template index within the group
     p.dbg_col = dbg_acc ? (int)(dbg_colidx % tc.nb) : -1;
+    p.dbg_xlast = a.r_w - (int)((dbg_acc && (uint32_t)dbg_pos >= tc.n_tpl0) ? tc.n_w2 : tc.n_w);
     {
         const char *dm = getenv("FOCR_TC_DBG");
         p.dbg_mode = dm ? atoi(dm) : 0;
@@ -1165,15 +1253,17 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         cudaMemcpyToSymbolAsync(g_wdlog, &wdlog, sizeof(wdlog), 0, cudaMemcpyHostToDevice, st);
     }
     const char *trace_path = dbg_acc ? nullptr : getenv("FOCR_TC_TRACE");
-        for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
+    for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != dbg_colidx / tc.nb) continue;
         if (trace_path && cudaMalloc((void **)&p.trace, (size_t)64 * 8) == cudaSuccess)
             cudaMemsetAsync(p.trace, 0, (size_t)64 * 8, st);
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
         p.colconst = tc.consts + (size_t)blk * tc.nb;
         p.col_base = blk * tc.nb;
-        p.bmax = tc.blk_bmax[blk] * 1.001f;
-        p.amax = std::max(p.thr * tc.blk_normmax[blk], 0.f) * 1.001f;
+        for (int c = 0; c < 2; c++) {
+            p.bmax[c] = tc.blk_bmax[c][blk] * 1.001f;
+            p.amax[c] = std::max(p.thr * tc.blk_normmax[c][blk], 0.f) * 1.001f;
+        }
         scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -1190,8 +1280,8 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
                         tc.n_h, p.nb, p.nbuf, p.ring, wdh[1], wdh[2], cta, wdh[4]);
                 uint32_t pg[32];
                 cudaMemcpyFromSymbol(pg, g_wdprog, sizeof(pg));
-                fprintf(stderr, "   progress snapshot of CTA %u (taken by warp %u, tag %u): T0 stage %u o %u | T1 stage %u o %u | toeplitz g0", wdh[7], wdh[8],
-                        wdh[9], pg[1] >> 24, pg[1] & 0xFFFFFF, pg[2] >> 24, pg[2] & 0xFFFFFF);
+                fprintf(stderr, "   progress snapshot of CTA %u (taken by warp %u, tag %u): issuer stage %u o %u | toeplitz g0", wdh[7], wdh[8],
+                        wdh[9], pg[1] >> 24, pg[1] & 0xFFFFFF);
                 for (int w = 4; w < 8; w++) fprintf(stderr, " %u", pg[w]);
                 fprintf(stderr, " | a2 o0");
                 for (int w = 8; w < 12; w++) fprintf(stderr, " %u", pg[w]);
@@ -1227,18 +1317,21 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         ca.cand_max = a.cand_max;
         ca.tpl_of = tc.tpl_of;
         ca.cls_of = tc.cls_of;
-        ca.rows = a.cls.rows;
+        ca.rows = tc.rows;
         ca.tpl = a.tpl;
         ca.inv = a.inv;
         ca.inv_page_stride = a.inv_page_stride;
         ca.pitch = a.pitch;
-        ca.n_w = tc.n_w;
         ca.n_h = tc.n_h;
         ca.np = tc.np;
-        ca.sp = a.sp;
+        ca.n_w[0] = tc.n_w;
+        ca.n_w[1] = tc.ncls == 2 ? tc.n_w2 : tc.n_w;
+        ca.sp[0] = p.sp[0];
+        ca.sp[1] = p.sp[1];
         ca.spitch = a.spitch;
         ca.plane_page_stride = a.plane_page_stride;
-        ca.n_d = (double)(tc.n_w * tc.n_h);
+        ca.n_d[0] = (double)(ca.n_w[0] * tc.n_h);
+        ca.n_d[1] = (double)(ca.n_w[1] * tc.n_h);
         ca.thr_d = a.thr_d;
         ca.sink = a.sink;
         if (hook) hook->exact_begin();
