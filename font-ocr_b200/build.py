@@ -42,21 +42,26 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    dg = _digest() + ("+exp" if os.environ.get("FOCR_TC_EXPERIMENTS") else "")
-    if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read() == dg:
-        return OUT
+    """Build the product library.  With FOCR_TC_EXPERIMENTS=1 in the environment the kernel's experiment hooks are compiled
+    in and the result goes to libfocr_b200_exp.so (tools/ select it with FOCR_B200_LIB); the product library is untouched."""
+    exp = bool(os.environ.get("FOCR_TC_EXPERIMENTS"))
+    out = OUT.replace(".so", "_exp.so") if exp else OUT
+    stamp = out + ".stamp"
+    dg = _digest() + ("+exp" if exp else "")
+    if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = ["-DFOCR_TC_EXPERIMENTS"] if os.environ.get("FOCR_TC_EXPERIMENTS") else []  # tools/tc_trace.py, tools/tc_modes.py
+    extra = ["-DFOCR_TC_EXPERIMENTS"] if exp else []  # tools/tc_trace.py, tools/tc_modes.py, tools/tc_timeline.py
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libfocr_b200.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    open(STAMP, "w").write(dg)
-    return OUT
+    open(stamp, "w").write(dg)
+    return out
 
 
 if __name__ == "__main__":

@@ -64,11 +64,10 @@ namespace cg = cooperative_groups;
 
 namespace focr {
 
-constexpr int TC_EPI_GROUPS = 4;      // epilogue warps per TMEM lane quarter
-constexpr int TC_EPI_WARPS = 4 * TC_EPI_GROUPS;
+constexpr int TC_EPI_WARPS = 8;       // epilogue warps: 2 teams (alternate jobs) x 4 TMEM lane quarters
 constexpr int TC_THREADS = 384 + 32 * TC_EPI_WARPS;
 static_assert(TC_LISTS_PER_CTA == TC_EPI_WARPS, "scan_tc.cuh: candidate lists per CTA = epilogue warps");
-static_assert(TC_EPI_GROUPS == 4, "the epilogue is written for 2 teams x 2 warps per lane quarter");
+constexpr int TC_EPI_UNITS = 4;       // 32-column units an epilogue warp holds in registers at a time
 constexpr int TC_G = 4;               // rows per pipeline group: one mbarrier handshake per 4 rows
 constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
 constexpr int TC_RAW_SLOTS = TC_RAW_GROUPS * TC_G;
@@ -78,13 +77,13 @@ constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: up to 4 groups x 4 output rows x 2 KB (2 for tall boxes)
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
 constexpr int TC_YSEG = 128;          // output rows per work item (fewer on small batches, see launch_scan_tc)
-// setmaxnreg budget (the kernel is compiled for 72 registers x 896 threads): warps 0-3 (TMA producer, MMA issuer) keep
-// 64, Toeplitz warps 40, A2 warps 48, epilogue warps 88: 128 x (64 + 40 + 48) + 512 x 88 = 64512 (an exact fit of
-// 65536 made setmaxnreg.inc wait for ever)
+// setmaxnreg budget (the kernel is launched with 96 registers x 640 threads = 61440): warps 0-3 (TMA producer, MMA
+// issuers: their state lives in uniform registers) keep 56, Toeplitz warps 40, A2 warps 48, and the 8 epilogue warps, which
+// hold four 32-column units at a time, take 168: 128 x (56 + 40 + 48) + 256 x 168 = 61440
 constexpr int TC_REGS_TOEPLITZ = 40;
 constexpr int TC_REGS_A2 = 48;
-constexpr int TC_REGS_EPILOGUE = 88;
-constexpr int TC_REGS_ISSUE = 64;
+constexpr int TC_REGS_EPILOGUE = 168;
+constexpr int TC_REGS_ISSUE = 56;
 constexpr size_t TC_SMEM_BUDGET = 220 * 1024;
 constexpr float TC_C0 = 16711680.f;               // 2^15 * 510 = 2^24 - 2^16: the constant term of the fp16 MMA
 constexpr float TC_KCAP = 8323072.f - 8192.f;     // C0 - 2^23 minus slack: largest b*S + a*P that keeps F in [2^23, 2^24)
@@ -130,6 +129,8 @@ struct TcParams {
     unsigned int *wd;   // watchdog words (see mbar_wait): [0] raised, [1] tag, [2] info, [3] CTA, [4] warp, [5] parity
     long long *trace;   // timing experiments (env FOCR_TC_TRACE=file): CTA 0's roles add up the cycles they spend in each
                         // wait / phase, [64] (tools/tc_trace.py names the slots)
+    int timeline;       // timing experiments: record the event timeline instead of the role time budget
+    uint32_t tl0;       // first job of the timeline window
     int dbg_mode;       // timing experiments only (env FOCR_TC_DBG, a bit mask; results are wrong when non-zero):
                         // 1 epilogue skips the TMEM reads, 2 epilogue loads but does not screen, 4 no MMAs are issued,
                         // 8 A2 rows skip their global loads, 16 no Toeplitz expansion, 32 A2 rows skip their stores
@@ -352,7 +353,14 @@ constexpr bool TC_EXP = false;
             __VA_ARGS__;                            \
         }                                           \
     } while (0)
-#define TT_BEGIN() const bool tron = TC_EXP && p.trace != nullptr && blockIdx.x == 0; long long tacc[6] = {0, 0, 0, 0, 0, 0}; const long long tstart_ = tron ? clock64() : 0
+#define TT_BEGIN() const bool tron = TC_EXP && p.trace != nullptr && blockIdx.x == 0 && !p.timeline; long long tacc[6] = {0, 0, 0, 0, 0, 0}; const long long tstart_ = tron ? clock64() : 0
+// event timeline (env FOCR_TC_TIMELINE=first job): CTA 0 stamps clock64 at event `ev` (0..3) of jobs [tl0, tl0+256) per role
+constexpr int TC_TL_JOBS = 256;
+#define TL(role, job, ev)                                                                                          \
+    do {                                                                                                           \
+        if (TC_EXP && p.timeline && blockIdx.x == 0 && (uint32_t)((job) - p.tl0) < (uint32_t)TC_TL_JOBS)         \
+            p.trace[64 + (((role) * TC_TL_JOBS + ((job) - p.tl0)) * 4 + (ev))] = clock64();                       \
+    } while (0)
 #define TT_END(base)                                                         \
     do {                                                                     \
         if (tron) {                                                          \
@@ -413,20 +421,31 @@ struct TcSmem {   // shared-memory addresses (shared window, bytes) of the opera
     volatile uint32_t *prog;
 };
 
-// ONE warp (warp 1) issues every job in order: job k (output row k / nsub, sub-block k % nsub) goes to accumulator
-// k mod nbuf.  The tensor pipe executes MMAs in issue order, so the warp only has to stay ahead of it: its per-job stream
-// is one wait (the accumulator's "empty" barrier, usually long since complete when the ring has three entries), 1 + KS
-// MMAs and one commit.  The row's operands (ring slots, A2 row) are shared by its jobs.
-// The warp runs CONVERGED and everything it computes depends only on kernel parameters and loop counters, so ptxas keeps
+// TWO issuing warps (warps 1 and 2): warp `mw` issues the jobs whose index has parity mw; job k (output row k / nsub,
+// sub-block k % nsub) goes to accumulator k mod nbuf and is drained by epilogue team k & 1.  tcgen05.mma blocks its issuer
+// at the rate of the tensor pipe (measured: the 8 MMAs of a 160-column job take ~690 cycles to ISSUE, there is next to no
+// queue), so whatever else an issuer does -- barrier waits (~100+ cycles even when complete), commits, ring hand-backs --
+// is dead time for the pipe unless ANOTHER warp is issuing meanwhile.  The two warps touch different accumulators, so
+// the order in which the pipe takes their MMAs is free.
+// Barriers: every accumulator has one "full" and one "empty" barrier PER PIPELINE: t_full[acc][i] is committed by issuer
+// i and waited on by team i; t_empty[acc][i] collects the arrivals of the team that drains the job which issuer i will
+// overwrite (the job nbuf earlier).  Each barrier has exactly one waiter that sees every one of its phases, whatever
+// the ring length (with an odd ring a shared barrier would be waited on by alternating parties, which can fall two phases
+// behind -- a parity wait then aliases).  A waiter keeps the parity of its next phase per accumulator in a bit mask.
+// A ring group goes back to its producer when BOTH warps have moved past it: each commits to the group's "empty" barrier
+// (count 2) when it reaches a job that no longer reads the group -- tcgen05.commit only tracks the committing thread's MMAs.
+// The warps run CONVERGED and everything they compute depends only on kernel parameters and loop counters, so ptxas keeps
 // the whole role in uniform registers (descriptor arithmetic = UIADD3, no R2UR); `leader` (elect.sync) guards the
 // tcgen05 instructions, which are uniform-datapath instructions executed once per warp.
-// KS = K steps per output row as a compile-time constant (0: generic loop): the issue sequence is straight-line
-// code, and because the ring stores its first n_hp-1 slots twice, every descriptor of a row is the first one plus
-// a constant.
+// Because the ring stores its first n_hp-1 slots twice, the slots of an output row are consecutive (no wrap test fires
+// inside a row when np == 16).
 // LEAN = no parity probe (the common case): the fp16 MMA is always issued, no run-time switches in the issue sequence.
-template <int KS, bool LEAN>
+// MW = which of the two issuing warps, a compile-time constant (a run-time warp index would sit in a vector register and
+// drag the barrier addresses and the job-ownership branch out of the uniform datapath).
+template <bool LEAN, uint32_t MW>
 __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t leader)
 {
+    constexpr uint32_t mw = MW;
     const uint32_t idesc8 = (2u << 4)                          // D format: S32
                             | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
                             | (0u << 15) | (0u << 16)          // A, B: K-major
@@ -458,63 +477,83 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
     const bool wrap = p.n_mirror == 0;       // no mirror slots: a row's K steps may run past the end of the ring
     const uint32_t mma_on = (TC_EXP && (p.dbg_mode & 4)) ? 0u : leader;
     const uint32_t f16_on = corr ? mma_on : 0u;
+    const uint32_t t_full = sm.t_full + 8 * mw, t_empty = sm.t_empty + 8 * mw;   // this pipeline's barriers: [acc][2]
     volatile uint32_t *const prog_ = sm.prog;
-    mbar_wait_addr(sm.bar_btile, 0, p.wd, 10, 0);
+    mbar_wait_addr(sm.bar_btile, 0, p.wd, 10 + mw, 0);
     TT_BEGIN();
-    uint32_t o = 0;                          // global output-row index of the next row
+    uint32_t o = 0;                          // global output-row index of the current row
     uint32_t g = 0;                          // global page-row index of that row's first page row
     uint32_t a_first = a_lo0;                // A descriptor (low word) of that page row's ring slot
     uint32_t o_slot16 = a2_addr16;           // A2 ring slot address (>> 4) of that output row
     uint32_t rel_g = 0, rel_rows = TC_G;     // page-row groups: next to hand back / rows covered once it is
     uint32_t new_g = 0, new_par = 0, rows_ready = 0;
     uint32_t rel2_g = 0, rel2_rows = TC_G, new2_g = 0, new2_par = 0, rows2_ready = 0;
-    uint32_t acc = 0, accpar = 0;            // the next job's accumulator and the phase of its barriers
-    bool first_round = true;
+    uint32_t job = 0, acc = 0;               // the current job and its accumulator (job mod nbuf)
+    uint32_t empty_par = 0;                  // bit a: parity of this warp's next phase of t_empty[a][mw]
     Item it;
     for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
         const uint32_t n_out_rows = it.ys1 - it.ys0;
         for (uint32_t j = 0; j < n_out_rows; j++) {
-            TC_PROG(1, (1u << 24) | o);
-            // operands: page rows g .. g+n_hp-1 and the A2 row of this output
-            while (rows_ready < g + n_hp) {
-                TT(0, mbar_wait_addr(sm.a_full + 8 * new_g, new_par, p.wd, 12, o, sm.prog));
-                rows_ready += TC_G;
-                if (++new_g == ring_g) new_g = 0, new_par ^= 1;
-            }
-            while (corr && rows2_ready <= o) {
-                TT(1, mbar_wait_addr(sm.a2_full + 8 * new2_g, new2_par, p.wd, 14, o, sm.prog));
-                rows2_ready += TC_G;
-                if (++new2_g == a2_groups) new2_g = 0, new2_par ^= 1;
-            }
             // one job per sub-block: the row's operands are shared, the templates (B, B2) and the accumulator differ
             uint32_t b_lo = b_lo0, b2 = b2_lo;
-            for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub) {
-                const uint32_t d0 = acc * nbs;
-                TC_PROG(1, (2u << 24) | o);
-                if (!first_round) TT(2, mbar_wait_addr<false>(sm.t_empty + 8 * acc, accpar ^ 1, p.wd, 16, o, sm.prog));
-                tc_fence_after();
-                const long long ti_ = tron ? clock64() : 0;
-                // F = A2 . B2^T in fp32 (accumulate off): K = 16 fp16 = two 16-byte chunks, one per box size
-                tc_mma_f16_overwrite_if(f16_on, d0, desc_hi | (o_slot16 | a2_lbo), desc_hi | b2, idesc16);
-                // K steps: consecutive ring slots (no wrap inside a row), consecutive B chunks
-                if (KS > 0) {
-#pragma unroll
-                    for (int k = 0; k < KS; k++)
-                        tc_mma_i8_if(mma_on, d0, desc_hi | (a_first + k * a_inc), desc_hi | (b_lo + k * b_inc), idesc8,
-                                     (corr || k) ? 1u : 0u);
-                } else {
-                    uint32_t al = a_first;
-                    for (uint32_t k = 0; k < ksteps; k++) {
-                        tc_mma_i8_if(mma_on, d0, desc_hi | al, desc_hi | (b_lo + k * b_inc), idesc8, (corr || k) ? 1u : 0u);
-                        al += a_inc;
-                        if (wrap && al >= a_end) al -= a_wrap;
+            for (uint32_t sb = 0; sb < nsub; sb++, b_lo += b_sub, b2 += b2_sub, job++) {
+                if ((job & 1u) == mw) {
+                    TC_PROG(1 + mw, (1u << 24) | o);
+                    // ring groups that lie entirely below this row are no longer read by this warp
+                    while (rel_rows <= g) {
+                        TT(4, tc_commit(leader, sm.a_empty + 8 * rel_g));
+                        rel_rows += TC_G;
+                        if (++rel_g == ring_g) rel_g = 0;
                     }
+                    while (rel2_rows <= o) {
+                        TT(4, tc_commit(leader, sm.a2_empty + 8 * rel2_g));
+                        rel2_rows += TC_G;
+                        if (++rel2_g == a2_groups) rel2_g = 0;
+                    }
+                    // operands: page rows g .. g+n_hp-1 and the A2 row of this output
+                    while (rows_ready < g + n_hp) {
+                        TT(0, mbar_wait_addr(sm.a_full + 8 * new_g, new_par, p.wd, 12 + mw, o, sm.prog));
+                        rows_ready += TC_G;
+                        if (++new_g == ring_g) new_g = 0, new_par ^= 1;
+                    }
+                    while (corr && rows2_ready <= o) {
+                        TT(1, mbar_wait_addr(sm.a2_full + 8 * new2_g, new2_par, p.wd, 14 + mw, o, sm.prog));
+                        rows2_ready += TC_G;
+                        if (++new2_g == a2_groups) new2_g = 0, new2_par ^= 1;
+                    }
+                    const uint32_t d0 = acc * nbs;
+                    TC_PROG(1 + mw, (2u << 24) | o);
+                    if (leader) TL(mw, job, 0);
+                    if (job >= nbuf) {   // the accumulator's previous job has been drained
+                        TT(2, mbar_wait_addr<false>(t_empty + 16 * acc, (empty_par >> acc) & 1u, p.wd, 16 + mw, o, sm.prog));
+                        empty_par ^= 1u << acc;
+                    }
+                    tc_fence_after();
+                    if (leader) TL(mw, job, 1);
+                    const long long ti_ = tron ? clock64() : 0;
+                    // F = A2 . B2^T in fp32 (accumulate off): K = 16 fp16 = two 16-byte chunks, one per box size
+                    tc_mma_f16_overwrite_if(f16_on, d0, desc_hi | (o_slot16 | a2_lbo), desc_hi | b2, idesc16);
+                    // K steps: consecutive ring slots, consecutive B chunks.  A rolled loop: in uniform registers a step is two
+                    // UIADD3, a compare and the UTCIMMA, far below the ~80 cycles the pipe takes per MMA (and a few small
+                    // instantiations keep ptxas' uniform-register allocation intact; four unrolled variants did not).
+                    {
+                        uint32_t al = a_first, bl = b_lo;
+#pragma unroll 1
+                        for (uint32_t k = 0; k < ksteps; k++) {
+                            tc_mma_i8_if(mma_on, d0, desc_hi | al, desc_hi | bl, idesc8, (corr || k) ? 1u : 0u);
+                            al += a_inc;
+                            bl += b_inc;
+                            if (wrap && al >= a_end) al -= a_wrap;
+                        }
+                    }
+                    if (tron) tacc[3] += clock64() - ti_;
+                    if (leader) TL(mw, job, 2);
+                    TT(4, tc_commit(leader, t_full + 16 * acc));   // accumulator ready for this pipeline's epilogue team
+                    if (leader) TL(mw, job, 3);
                 }
-                if (tron) tacc[3] += clock64() - ti_;
-                TT(4, tc_commit(leader, sm.t_full + 8 * acc));   // accumulator ready for the epilogue
-                if (++acc == nbuf) acc = 0, accpar ^= 1, first_round = false;
+                if (++acc == nbuf) acc = 0;
             }
-            // bookkeeping for the next row (off the critical path: the tensor pipe is busy with this row)
+            // next row
             o++;
             g++;
             o_slot16 += a2_slot16;
@@ -526,23 +565,18 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
                 a_first += (n_hp - 1) * pitch16;
                 if (a_first >= a_end) a_first -= a_wrap;
             }
-            // hand back every group that lies entirely below what the next output reads
-            while (rel_rows <= g) {
-                TT(4, tc_commit(leader, sm.a_empty + 8 * rel_g));
-                rel_rows += TC_G;
-                if (++rel_g == ring_g) rel_g = 0;
-            }
-            while (rel2_rows <= o) {
-                TT(4, tc_commit(leader, sm.a2_empty + 8 * rel2_g));
-                rel2_rows += TC_G;
-                if (++rel2_g == a2_groups) rel2_g = 0;
-            }
         }
     }
-    TC_PROG(1, 9u << 24);
-    if (leader) TT_END(0);
+    TC_PROG(1 + mw, 9u << 24);
+    // groups this warp never passed explicitly (the last rows): nothing waits for them
+    if (leader && mw == 0) TT_END(0);
 }
 
+// NUNITS = 32-column units per accumulator (p.nunits) as a compile-time constant: the epilogue warps run a latency-bound
+// instruction stream (two of them per SM sub-partition), and every run-time "is there a unit b" test in it costs a
+// constant load, a compare, a branch and often an instruction-cache miss (ncu: ~400 instructions per job with run-time
+// tests against ~150 without).
+template <int NUNITS>
 __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_constant__ TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -560,10 +594,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
     uint64_t *a_empty = a_full + TC_RING_MAX;         // TC_RING_MAX
     uint64_t *a2_full = a_empty + TC_RING_MAX;        // TC_A2_GROUPS
     uint64_t *a2_empty = a2_full + TC_A2_GROUPS;      // TC_A2_GROUPS
-    uint64_t *t_full = a2_empty + TC_A2_GROUPS;       // TC_MAX_BUF
-    uint64_t *t_empty = t_full + TC_MAX_BUF;          // TC_MAX_BUF
-    uint32_t *tmem_ptr = (uint32_t *)(t_empty + TC_MAX_BUF);
+    uint64_t *t_full = a2_empty + TC_A2_GROUPS;       // [TC_MAX_BUF][2]: per accumulator and pipeline (issuing warp / epilogue team)
+    uint64_t *t_empty = t_full + 2 * TC_MAX_BUF;      // [TC_MAX_BUF][2]
+    uint32_t *tmem_ptr = (uint32_t *)(t_empty + 2 * TC_MAX_BUF);
     volatile uint32_t *prog = (volatile uint32_t *)(tmem_ptr + 2);   // [32] per-warp progress (debugging aid, see mbar_wait)
+    // (73 barriers + tmem_ptr[2] + prog[32] = 720 bytes after a 128-byte aligned start: the scratch is 16-byte aligned)
+    uint8_t *epi_scratch = (uint8_t *)(tmem_ptr + 2 + 32);   // [TC_EPI_WARPS][128 B] candidate extraction
     if (threadIdx.x < 32) prog[threadIdx.x] = 0;
     volatile uint32_t *const prog_ = prog;
 
@@ -579,15 +615,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         for (int i = 0; i < TC_RING_MAX; i++) {
             mbar_init(a_full + i, 4);
-            mbar_init(a_empty + i, 1);     // one tcgen05.commit of the MMA-issuing thread
+            mbar_init(a_empty + i, 2);     // one tcgen05.commit per MMA-issuing warp
         }
         for (int i = 0; i < TC_A2_GROUPS; i++) {
             mbar_init(a2_full + i, 4);     // one arrival per A2 warp
-            mbar_init(a2_empty + i, 1);
+            mbar_init(a2_empty + i, 2);
         }
-        for (int i = 0; i < TC_MAX_BUF; i++) {
+        for (int i = 0; i < 2 * TC_MAX_BUF; i++) {
             mbar_init(t_full + i, 1);
-            mbar_init(t_empty + i, TC_EPI_WARPS / 2);  // one arrival per epilogue warp of the team that drains the job
+            mbar_init(t_empty + i, TC_EPI_WARPS / 2);  // one arrival per epilogue warp (lane quarter) of the team that drains the job
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -672,8 +708,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         }
         if (in_group != 0 && elect_one()) mbar_arrive(raw_full + rg);  // the last, partial group
         if (lane == 0) TT_END(32);
-    } else if (warp == 1) {
-        // ================================================================== MMA issuer (tc_mma_role): the whole warp, converged
+    } else if (warp == 1 || warp == 2) {
+        // ================================================================== MMA issuers (tc_mma_role): whole warps, converged
         const uint32_t sbase = smem_u32(smem);
         const TcSmem sm = {sbase + (uint32_t)(btile - smem), sbase + (uint32_t)(ring - smem), sbase + (uint32_t)(a2ring - smem),
                            sbase + (uint32_t)(b2tile - smem), sbase + (uint32_t)((uint8_t *)bar_btile - smem),
@@ -681,11 +717,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                            sbase + (uint32_t)((uint8_t *)a2_full - smem), sbase + (uint32_t)((uint8_t *)a2_empty - smem),
                            sbase + (uint32_t)((uint8_t *)t_full - smem), sbase + (uint32_t)((uint8_t *)t_empty - smem), prog};
         const uint32_t leader = elect_flag();
-        switch (p.n_mirror && p.dbg_acc == nullptr ? p.ksteps : 0) {   // the unrolled issue sequences assume consecutive slots (mirrored ring)
-            case 6: tc_mma_role<6, true>(p, sm, leader); break;
-            case 7: tc_mma_role<7, true>(p, sm, leader); break;
-            case 8: tc_mma_role<8, true>(p, sm, leader); break;
-            default: tc_mma_role<0, false>(p, sm, leader); break;
+        const bool lean = p.dbg_acc == nullptr;
+        if (warp == 1) {
+            if (lean) tc_mma_role<true, 0>(p, sm, leader);
+            else tc_mma_role<false, 0>(p, sm, leader);
+        } else {
+            if (lean) tc_mma_role<true, 1>(p, sm, leader);
+            else tc_mma_role<false, 1>(p, sm, leader);
         }
         __syncwarp();
     }
@@ -807,118 +845,135 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         if (w == 0 && lane == 0) TT_END(24);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPILOGUE));
-        // ================================================================== epilogue (16 warps = 2 teams x 4 lane quarters x 2)
+        // ================================================================== epilogue (8 warps = 2 teams x 4 lane quarters)
         // The accumulator holds the bits of fp32 C0 + d: one 3-input max per column pair (a tree, so the
-        // FMNMX3s are independent), one vote per 32 columns.  Jobs alternate between two TEAMS of 8 warps, so a
-        // warp pays the per-job overhead (barrier wait, fences, arrive) only every second job; inside a team the two
-        // warps of a lane quarter take one half of the job's columns each, as chunks of 32 (+ one of 16).  Two chunks
-        // are in registers at a time; the accumulator goes back to the MMA warp as soon as the warp's LAST chunk has
-        // landed, before it is screened.
+        // FMNMX3s are independent), one vote per 32 columns.  Jobs alternate between two TEAMS of 4 warps (one per TMEM
+        // lane quarter); a warp takes ALL columns of its job's lane quarter, up to four 32-column units in registers at
+        // once, and hands the accumulator back to the MMA warps as soon as its last unit has landed -- before it screens
+        // (jobs of more than four units: the first ones are screened while the last ones load).  The warps of a team
+        // do not synchronise with each other: each polls the job's "full" barrier itself, so a warp that is busy
+        // extracting candidates delays nobody else.
         const int e = warp - 12;
         const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
-        const int team = (e >> 2) & 1, half = e >> 3;   // team = which jobs, half = which half of a job's columns
+        const int team = e >> 2;                  // which jobs
         const int m = q * 32 + lane;              // window within the strip
         const uint32_t nbuf = p.nbuf, nsub = p.nsub;
-        const int cols_w = p.nbs >> 1;            // columns per warp (a multiple of 16)
-        const int n32 = cols_w >> 5, nch = n32 + ((cols_w >> 4) & 1);   // full chunks, chunks incl. the 16-column tail (<= 4)
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * cols_w);
+        constexpr int nunits = NUNITS, n2 = nunits - TC_EPI_UNITS;   // n2 > 0: units screened before the release
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         const float T = p.dbg_acc ? 3.0e38f : TC_C0 - TC_MARGIN;
-        uint32_t acc = 0, accpar = 0;             // the next job's accumulator and phase (as in tc_mma_role)
+        uint32_t acc = 0;                         // the next job's accumulator (as in tc_mma_role)
         uint32_t job = 0;
+        uint32_t full_par = 0;                    // bit a: parity of this team's next phase of t_full[a][team]
+        const uint32_t next_pipe = (uint32_t)(team + (int)p.nbuf) & 1u;   // pipeline of the job that overwrites an accumulator this team drains
         Hit *my_list = p.cands + (size_t)(blockIdx.x * TC_LISTS_PER_CTA + e) * p.cand_cap;
         uint32_t my_count = 0;
+        float *const scratch = (float *)(epi_scratch + e * 128);   // one lane's 32 values at a time (candidate extraction)
+        const unsigned lane_lt = (1u << lane) - 1u;
         const bool no_ld = TC_EXP && (p.dbg_mode & 1), no_screen = TC_EXP && (p.dbg_mode & 2);
         const int dbg_sub = p.dbg_acc ? p.dbg_col / p.nbs : -1, dbg_c = p.dbg_acc ? p.dbg_col % p.nbs : 0;
-        const bool h0 = !no_ld, h1 = nch > 1 && !no_ld, h2 = nch > 2 && !no_ld, h3 = nch > 3 && !no_ld;
         TT_BEGIN();
         Item it;
         for (int idx = blockIdx.x; get_item(p, idx, it); idx += gridDim.x) {
-            const int gx = it.x0 + m;
+            const int gx0 = it.x0 + q * 32;       // window of lane 0
             for (int y = it.ys0; y < it.ys1; y++) {
               for (uint32_t sb = 0; sb < nsub; sb++, job++) {
                 if ((job & 1u) == (uint32_t)team) {
                 if (lane == 0) TC_PROG(warp, job);
-                // ONE warp of the team polls the mbarrier (polling costs shared-memory bandwidth, which the tensor core's
-                // operand reads already use to ~80 %); its team-mates wait on a hardware named barrier
-                if (e == team * 4) TT(0, mbar_wait<false>(t_full + acc, accpar, p.wd, 20 + team, y, prog));
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(256) : "memory");
+                TT(0, mbar_wait<false>(t_full + 2 * acc + team, (full_par >> acc) & 1u, p.wd, 20 + team, y, prog));
+                full_par ^= 1u << acc;
                 tc_fence_after();
+                const int tlrole = e == 0 ? 2 : e == 4 ? 3 : 0;
+                if (tlrole && lane == 0) TL(tlrole, job, 0);
                 const long long tseen_ = tron ? clock64() : 0;
                 const uint32_t tb = tlane + acc * p.nbs;
-                const uint32_t cbase = p.col_base + sb * p.nbs + half * cols_w;
-                auto release = [&]() {  // every tcgen05.ld of this job has completed: hand the accumulator back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + acc);
-                    if (tron) tacc[3] += clock64() - tseen_;   // time from "accumulator full" seen to "accumulator released"
-                };
-                auto ld = [&](uint32_t (&v)[32], int c) {   // chunk c: 32 columns, or the 16-column tail
-                    if (c < n32) tc_ld32(tb + c * 32, v);
-                    else tc_ld16(tb + c * 32, v);
-                };
-                auto screen = [&](uint32_t (&v)[32], int c) {
-                    const bool full = c < n32;
-                    float t[6];
+                const uint32_t cbase = p.col_base + sb * p.nbs;
+                auto screen = [&](uint32_t (&v)[32], int u) {
+                    const long long ts_ = tron ? clock64() : 0;
+                    float t[11];
 #pragma unroll
-                    for (int j = 0; j < 5; j++)
+                    for (int j = 0; j < 10; j++)
                         asm("max.f32 %0, %1, %2, %3;"
                             : "=f"(t[j])
                             : "f"(__uint_as_float(v[3 * j])), "f"(__uint_as_float(v[3 * j + 1])), "f"(__uint_as_float(v[3 * j + 2])));
-                    t[5] = __uint_as_float(v[15]);
-                    float a, b, mx;
+                    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+                    float a, b, c, mx;
                     asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(t[0]), "f"(t[1]), "f"(t[2]));
                     asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(t[3]), "f"(t[4]), "f"(t[5]));
-                    mx = fmaxf(a, b);
-                    if (full) {   // warp-uniform
-                        float u[6];
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(c) : "f"(t[6]), "f"(t[7]), "f"(t[8]));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(t[9]), "f"(t[10]), "f"(a));
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(b), "f"(c));
+                    uint32_t hits = __ballot_sync(0xffffffffu, mx >= T);   // lanes (windows) with a survivor among these 32 columns
+                    // ~12 % of the units have one: the survivor lanes (few) are handled ONE AT A TIME, warp-wide: the lane
+                    // parks its 32 values in shared memory, every lane then tests one column, and the ballot is the
+                    // column mask -- each set lane appends its own candidate record (slots by popc prefix, no atomics)
+                    while (hits) {
+                        const int L = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (lane == L) {
 #pragma unroll
-                        for (int j = 0; j < 5; j++)
-                            asm("max.f32 %0, %1, %2, %3;"
-                                : "=f"(u[j])
-                                : "f"(__uint_as_float(v[16 + 3 * j])), "f"(__uint_as_float(v[17 + 3 * j])), "f"(__uint_as_float(v[18 + 3 * j])));
-                        u[5] = __uint_as_float(v[31]);
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(a) : "f"(u[0]), "f"(u[1]), "f"(u[2]));
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(b) : "f"(u[3]), "f"(u[4]), "f"(u[5]));
-                        asm("max.f32 %0, %1, %2, %3;" : "=f"(mx) : "f"(mx), "f"(a), "f"(b));
+                            for (int j = 0; j < 8; j++)
+                                ((uint4 *)scratch)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                        __syncwarp();
+                        const bool mine = scratch[lane] >= T;
+                        const unsigned vote = __ballot_sync(0xffffffffu, mine);
+                        if (mine) {
+                            const uint32_t slot = my_count + __popc(vote & lane_lt);
+                            if (slot < p.cand_cap) {
+                                Hit h;
+                                h.t = cbase + u * 32 + lane;
+                                h.yx = ((uint32_t)y << 16) | (uint32_t)(gx0 + L);
+                                h.sim = 0.f;
+                                h.page = it.page;
+                                my_list[slot] = h;
+                            }
+                        }
+                        my_count += __popc(vote);
+                        __syncwarp();
+                        if (tron) tacc[2]++;
                     }
-                    if (__any_sync(0xffffffffu, mx >= T)) {
-                        // rare: some lane of the warp has a survivor among these columns
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) mask |= (__uint_as_float(v[j]) >= T ? 1u : 0u) << j;
-                        if (!full) mask &= 0xFFFFu;
-                        append_candidates(my_list, p.cand_cap, my_count, mask, cbase + c * 32, it.page, gx, y);
-                    }
+                    if (tron) tacc[5] += clock64() - ts_;
                 };
-                if (p.dbg_acc && half == 0 && (int)sb == dbg_sub) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
-                    const uint32_t a = tc_ld1(tmem_base + ((uint32_t)(q * 32) << 16) + acc * p.nbs + dbg_c);
+                if (p.dbg_acc && (int)sb == dbg_sub) {  // parity probe: the raw numerator of one column (the fp16 MMA is off)
+                    const uint32_t a = tc_ld1(tb + dbg_c);
                     tc_wait_ld();
+                    const int gx = gx0 + lane;
                     if (gx >= 1 && gx <= p.dbg_xlast) p.dbg_acc[(size_t)y * p.r_w + gx] = a;
                 }
-                uint32_t va[32], vb[32];
-                if (h0) ld(va, 0);
-                if (h1) ld(vb, 1);
-                if (h0) tc_wait_ld32(va);
-                if (h1) tc_wait_ld32(vb);
-                // a warp with more than two chunks screens its first two while the next two are in flight; the last
-                // (or only) pair is screened after the accumulator has been released.  One common tail for both cases
-                // keeps the code small.
-                if (h2) {
-                    if (!no_screen) screen(va, 0);
-                    ld(va, 2);
-                    if (!no_screen) screen(vb, 1);
-                    if (h3) ld(vb, 3);
-                    tc_wait_ld32(va);
-                    if (h3) tc_wait_ld32(vb);
+                uint32_t v[TC_EPI_UNITS][32];
+#pragma unroll
+                for (int b = 0; b < TC_EPI_UNITS; b++)
+                    if (b < nunits && !no_ld) tc_ld32(tb + b * 32, v[b]);
+#pragma unroll
+                for (int b = 0; b < TC_EPI_UNITS; b++)
+                    if (b < nunits && !no_ld) tc_wait_ld32(v[b]);
+                if (tlrole && lane == 0) TL(tlrole, job, 1);
+                if (n2 > 0) {   // more than four units: screen the first ones, reload their registers with the last ones
+#pragma unroll
+                    for (int b = 0; b < TC_EPI_UNITS; b++)
+                        if (b < n2) {
+                            if (!no_screen) screen(v[b], b);
+                            if (!no_ld) tc_ld32(tb + (b + TC_EPI_UNITS) * 32, v[b]);
+                        }
+#pragma unroll
+                    for (int b = 0; b < TC_EPI_UNITS; b++)
+                        if (b < n2 && !no_ld) tc_wait_ld32(v[b]);
                 }
-                release();
+                // every tcgen05.ld of this job has completed: hand the accumulator back, then screen what is in registers
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + 2 * acc + next_pipe);
+                if (tlrole && lane == 0) TL(tlrole, job, 2);
+                if (tron) tacc[3] += clock64() - tseen_;   // time from "accumulator full" seen to "accumulator released"
                 if (!no_screen) {
-                    if (h2 || h0) screen(va, h2 ? 2 : 0);
-                    if (h2 ? h3 : h1) screen(vb, h2 ? 3 : 1);
+#pragma unroll
+                    for (int b = 0; b < TC_EPI_UNITS; b++)
+                        if (b < nunits) screen(v[b], b < n2 ? b + TC_EPI_UNITS : b);
                 }
                 if (tron) tacc[4] += clock64() - tseen_;       // ... to the end of the job (screens, candidates)
+                if (tlrole && lane == 0) TL(tlrole, job, 3);
                 }
-                if (++acc == nbuf) acc = 0, accpar ^= 1;
+                if (++acc == nbuf) acc = 0;
               }
             }
         }
@@ -1043,7 +1098,7 @@ static size_t tc_smem_bytes(uint32_t btile_bytes, int ring, int n_mirror, int ro
 {
     return ((btile_bytes + 127) & ~127u) + (size_t)(ring + n_mirror) * row_pitch + ((TC_RAW_SLOTS * TC_RAW_BYTES + 127) & ~127) +
            (size_t)a2_groups * TC_G * a2_slot + (size_t)2 * nb * 16 +
-           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 2 * TC_MAX_BUF) * 8 + 64 + 128;
+           (1 + 2 * TC_RAW_GROUPS + 2 * TC_RING_MAX + 2 * TC_A2_GROUPS + 4 * TC_MAX_BUF) * 8 + 64 + 128 + 16 + TC_EPI_WARPS * 128;
 }
 
 int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n_h, uint32_t np)
@@ -1235,7 +1290,19 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     if (const char *e = getenv("FOCR_TC_YSEG")) p.yseg = std::max(1, atoi(e));   // experiments
     p.n_ysegs = (ys + p.yseg - 1) / p.yseg;
     const size_t smem = tc_smem_bytes(p.btile_bytes, p.ring, p.n_mirror, p.row_pitch, p.nb, p.a2_groups, p.a2_slot);
-    cudaError_t e = cudaFuncSetAttribute(scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    void (*kernel)(const TcParams) = nullptr;
+    switch (p.nunits) {
+        case 1: kernel = scan_tc_kernel<1>; break;
+        case 2: kernel = scan_tc_kernel<2>; break;
+        case 3: kernel = scan_tc_kernel<3>; break;
+        case 4: kernel = scan_tc_kernel<4>; break;
+        case 5: kernel = scan_tc_kernel<5>; break;
+        case 6: kernel = scan_tc_kernel<6>; break;
+        case 7: kernel = scan_tc_kernel<7>; break;
+        case 8: kernel = scan_tc_kernel<8>; break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int items = n_pages * p.n_xstrips * p.n_ysegs;
     const int grid = std::min(items, sm_count);
@@ -1255,8 +1322,13 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     const char *trace_path = dbg_acc ? nullptr : getenv("FOCR_TC_TRACE");
     for (uint32_t blk = 0; blk < tc.n_blocks; blk++) {
         if (dbg_acc && blk != dbg_colidx / tc.nb) continue;
-        if (trace_path && cudaMalloc((void **)&p.trace, (size_t)64 * 8) == cudaSuccess)
-            cudaMemsetAsync(p.trace, 0, (size_t)64 * 8, st);
+        const size_t trace_words = 64 + (size_t)4 * TC_TL_JOBS * 4;
+        if (trace_path && cudaMalloc((void **)&p.trace, trace_words * 8) == cudaSuccess) {
+            cudaMemsetAsync(p.trace, 0, trace_words * 8, st);
+            const char *tl = getenv("FOCR_TC_TIMELINE");
+            p.timeline = tl != nullptr;
+            p.tl0 = tl ? (uint32_t)atoi(tl) : 0;
+        }
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
         p.colconst = tc.consts + (size_t)blk * tc.nb;
         p.col_base = blk * tc.nb;
@@ -1264,7 +1336,7 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
             p.bmax[c] = tc.blk_bmax[c][blk] * 1.001f;
             p.amax[c] = std::max(p.thr * tc.blk_normmax[c][blk], 0.f) * 1.001f;
         }
-        scan_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+        kernel<<<grid, TC_THREADS, smem, st>>>(p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (n_launches) (*n_launches)++;
@@ -1296,7 +1368,7 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
             cudaMemsetAsync(wdlog, 0, (size_t)grid * 32 * sizeof(uint4), st);
         }
         if (p.trace) {  // dump CTA 0's per-row timestamps: one file per (box size, N-block) launch, last launch wins
-            std::vector<long long> h(64);
+            std::vector<long long> h(trace_words);
             cudaStreamSynchronize(st);
             cudaMemcpy(h.data(), p.trace, h.size() * 8, cudaMemcpyDeviceToHost);
             cudaFree(p.trace);

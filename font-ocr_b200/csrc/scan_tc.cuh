@@ -7,7 +7,7 @@
 
 namespace focr {
 
-constexpr int TC_LISTS_PER_CTA = 16;  // epilogue warps per CTA, each with a private candidate list
+constexpr int TC_LISTS_PER_CTA = 8;   // epilogue warps per CTA, each with a private candidate list
 
 // A LAUNCH GROUP of the tcgen05 kernel: the templates of one box size, or of TWO box sizes of the same height and
 // padded row width (np).  The correlation GEMM does not see the box width (template rows are zero padded to np

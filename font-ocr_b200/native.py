@@ -8,7 +8,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfocr_b200.so")
+# FOCR_B200_LIB: tools/ load the experiments build (libfocr_b200_exp.so, see build.py) through this; the default is the product
+LIB_PATH = os.environ.get("FOCR_B200_LIB") or os.path.join(HERE, "libfocr_b200.so")
 
 MATCH_DTYPE = np.dtype([("x", np.uint16), ("y", np.uint16), ("similarity", np.float32)])  # focr_match
 RASTER_DTYPE = np.dtype([("offset", np.uint64), ("left", np.int16), ("top", np.int16),

@@ -23,7 +23,7 @@ for i in range(2):
 ctx.sync()
 rows = P * 20 * 3494 / 148.0  # output rows per CTA (approx.)
 roles = {0: ("mma", ["a_full", "a2_full", "t_empty", "issue", "commits"]),
-         8: ("epi0", ["t_full", "-", "-", "seen->released", "seen->job done"]),
+         8: ("epi0 (per own job = 2 rows' worth / nsub)", ["t_full", "slow screens (cycles)", "slow screens (count)", "seen->released", "seen->job done", "all screens"]),
          16: ("toeplitz0 (per 4 rows)", ["raw_full", "a_empty"]),
          24: ("a2_0 (per 4 rows)", ["a2_empty"]),
          32: ("tma", ["raw_empty"])}
