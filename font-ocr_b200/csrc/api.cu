@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -43,7 +44,7 @@ extern "C" void focr_get_limits(focr_limits *out)
     out->max_template_w = MAX_TPL_W;
     out->max_template_h = MAX_TPL_H;
     out->max_page_w = 15360;  // finalize_sel_cap: n_out + r_w keys must fit the shared-memory sort
-    out->max_page_h = 65535;
+    out->max_page_h = 65535 - PAGE_PAD_ROWS;  // stage_invert: grid.y = r_h + PAGE_PAD_ROWS <= 65535
     out->max_n_out = 4096;
 }
 
@@ -79,12 +80,43 @@ struct DevBuf {
     T *as() const { return (T *)p; }
 };
 
+struct PinBuf {  // library-owned pinned staging (grow-only)
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr, cap = 0;
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr, cap = 0;
+    }
+    template <class T>
+    T *as() const { return (T *)p; }
+};
+
+constexpr int FLAG_WORDS = 16;    // one 64-byte flag block per chunk
+constexpr int FLAG_BLOCKS = 64;   // chunks the device-resident scan may enqueue between two host checks
+
 struct Slot {  // everything one in-flight chunk of pages needs
     DevBuf gray, inv, sp, s2p, pf, rn, sp2, pf2, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
-    unsigned int *flags_host = nullptr;  // pinned: [0] hit_count, [1] overflow, [2] cand_count, [3] cand high-water mark,
-                                         // [4..9] scan_tc watchdog (raised, tag, info, CTA, warp, parity)
+    PinBuf gray_pin, out_pin, counts_pin;   // staging for callers whose host buffers are pageable (ncc.rs:575: a Rust Vec<u8>)
+    unsigned int *flags_host = nullptr;  // pinned, FLAG_BLOCKS blocks of: [0] hit_count, [1] overflow, [2] cand_count,
+                                         // [3] cand high-water mark, [4..9] scan_tc watchdog (raised, tag, info, CTA, warp, parity)
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_d2h = nullptr;
     uint32_t hits_per_page = 0;
+    uint32_t reserve_pages = 0;   // size the buffers for this many pages at once (a ramp of growing chunks would re-allocate)
 };
 
 struct focr_ctx {
@@ -176,8 +208,8 @@ extern "C" int focr_ctx_create(int device, focr_ctx **out)
     CU(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
     for (auto &s : c->slot) {
-        CU(cudaMallocHost((void **)&s.flags_host, 64));
-        memset(s.flags_host, 0, 64);
+        CU(cudaMallocHost((void **)&s.flags_host, FLAG_BLOCKS * FLAG_WORDS * 4));
+        memset(s.flags_host, 0, FLAG_BLOCKS * FLAG_WORDS * 4);
         CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_compute, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
@@ -195,6 +227,7 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
         for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.sp2, &s.pf2, &s.rowcount, &s.hits, &s.cands, &s.candcnt, &s.sel, &s.ycut,
                           &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
             b->release();
+        for (PinBuf *b : {&s.gray_pin, &s.out_pin, &s.counts_pin}) b->release();
         if (s.flags_host) cudaFreeHost(s.flags_host);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_compute) cudaEventDestroy(s.ev_compute);
@@ -393,7 +426,8 @@ struct Geometry {
 
 static int make_geometry(uint32_t r_w, uint32_t r_h, uint32_t n_out, Geometry &g)
 {
-    if (r_w == 0 || r_h == 0 || r_w > 65535 || r_h > 65535) return fail(FOCR_ERR_ARG, "page dimensions must fit u16");
+    if (r_w == 0 || r_h == 0 || r_w > 65535 || r_h > 65535 - PAGE_PAD_ROWS)
+        return fail(FOCR_ERR_ARG, "page dimensions must fit u16 (height <= 65533)");
     if (n_out == 0 || n_out > 4096) return fail(FOCR_ERR_ARG, "n_out must be in 1..4096");
     g.r_w = r_w;
     g.r_h = r_h;
@@ -414,10 +448,11 @@ static bool use_tc(const focr_ctx *c, const focr_bank *b, const ClassHost &ch)
     return tc_class_supported(b->groups[ch.group].tc);
 }
 
-// enqueue the whole device pipeline for nB pages that sit (gray or inverted) in device memory
+// enqueue the whole device pipeline for nB pages that sit (gray or inverted) in device memory; the chunk reports through
+// flag block `flag_block` of the slot (copied to the pinned mirror right away when copy_flags)
 static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometry &g, const uint8_t *pages_dev,
                          size_t page_stride, size_t in_pitch, uint32_t nB, float threshold, int invert,
-                         focr_match *out_dev, uint32_t *counts_dev)
+                         focr_match *out_dev, uint32_t *counts_dev, int flag_block = 0, bool copy_flags = true)
 {
     cudaStream_t st = c->stream;
     const uint32_t T = b->T;
@@ -433,28 +468,30 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     if (s.hits_per_page < c->hits_per_page) s.hits_per_page = c->hits_per_page;
     const size_t hit_cap = (size_t)s.hits_per_page * nB;
     const size_t PT = (size_t)nB * T;
-    CU(s.inv.ensure(g.inv_page_stride * nB));
-    CU(s.sp.ensure(g.plane_page_stride * nB * 4));
-    CU(s.pf.ensure(g.plane_page_stride * nB * 4));
+    const size_t nR = std::max(nB, s.reserve_pages), PTR = nR * T;   // allocation sizes
+    CU(s.inv.ensure(g.inv_page_stride * nR));
+    CU(s.sp.ensure(g.plane_page_stride * nR * 4));
+    CU(s.pf.ensure(g.plane_page_stride * nR * 4));
     if (any_simt) {   // only the SIMT kernel reads the sum-of-squares and f64 planes
-        CU(s.s2p.ensure(g.plane_page_stride * nB * 4));
-        CU(s.rn.ensure(g.plane_page_stride * nB * 8));
+        CU(s.s2p.ensure(g.plane_page_stride * nR * 4));
+        CU(s.rn.ensure(g.plane_page_stride * nR * 8));
     }
     if (any_tc && any_pair) {
-        CU(s.sp2.ensure(g.plane_page_stride * nB * 4));
-        CU(s.pf2.ensure(g.plane_page_stride * nB * 4));
+        CU(s.sp2.ensure(g.plane_page_stride * nR * 4));
+        CU(s.pf2.ensure(g.plane_page_stride * nR * 4));
     }
-    CU(s.rowcount.ensure(PT * g.r_h * 4));
-    CU(s.hits.ensure(hit_cap * sizeof(Hit)));
+    CU(s.rowcount.ensure(PTR * g.r_h * 4));
+    CU(s.hits.ensure((size_t)s.hits_per_page * nR * sizeof(Hit)));
     const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
     if (any_tc) {
         CU(s.cands.ensure(n_lists * c->cand_per_warp * sizeof(Hit)));
         CU(s.candcnt.ensure(n_lists * 4));
     }
-    CU(s.sel.ensure(PT * g.sel_cap * 8));
-    CU(s.ycut.ensure(PT * 4));
-    CU(s.selcount.ensure(PT * 4));
-    CU(s.flags.ensure(64));
+    CU(s.sel.ensure(PTR * g.sel_cap * 8));
+    CU(s.ycut.ensure(PTR * 4));
+    CU(s.selcount.ensure(PTR * 4));
+    CU(s.flags.ensure(FLAG_BLOCKS * FLAG_WORDS * 4));
+    unsigned int *const flags = s.flags.as<unsigned int>() + (size_t)flag_block * FLAG_WORDS;
 
     {
         StageTimer tm(c, FOCR_STAGE_INVERT);
@@ -464,12 +501,12 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     c->launches++;
     CU(cudaMemsetAsync(s.rowcount.p, 0, PT * g.r_h * 4, st));
     CU(cudaMemsetAsync(s.selcount.p, 0, PT * 4, st));
-    CU(cudaMemsetAsync(s.flags.p, 0, 64, st));
+    CU(cudaMemsetAsync(flags, 0, FLAG_WORDS * 4, st));
 
     HitSink sink;
     sink.hits = s.hits.as<Hit>();
     sink.hit_cap = (uint32_t)std::min<size_t>(hit_cap, 0xFFFFFFFFu);
-    sink.hit_count = s.flags.as<unsigned int>();
+    sink.hit_count = flags;
     sink.rowcount = s.rowcount.as<unsigned int>();
     sink.T = T;
     sink.r_h = g.r_h;
@@ -531,7 +568,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.cands = s.cands.as<Hit>();
         a.cand_cap = c->cand_per_warp;
         a.cand_count = s.candcnt.as<unsigned int>();
-        a.cand_max = s.flags.as<unsigned int>() + 3;
+        a.cand_max = flags + 3;
         a.acc_out = nullptr;
         if (tc) CU(cudaMemsetAsync(a.cand_count, 0, n_lists * 4, st));
         int nl = 0;
@@ -566,14 +603,14 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
 
     FinalizeArgs f;
     f.hits = s.hits.as<Hit>();
-    f.hit_count = s.flags.as<unsigned int>();
+    f.hit_count = flags;
     f.hit_cap = sink.hit_cap;
     f.rowcount = s.rowcount.as<unsigned int>();
     f.y_cut = s.ycut.as<uint32_t>();
     f.sel_count = s.selcount.as<unsigned int>();
     f.sel = s.sel.as<unsigned long long>();
     f.sel_cap = g.sel_cap;
-    f.overflow = s.flags.as<unsigned int>() + 1;
+    f.overflow = flags + 1;
     f.T = T;
     f.r_h = g.r_h;
     f.n_pages = nB;
@@ -586,31 +623,33 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         CU(launch_finalize(f, st, &nl));
     }
     c->launches += nl;
-    CU(cudaMemcpyAsync(s.flags_host, s.flags.p, 64, cudaMemcpyDeviceToHost, st));
+    if (copy_flags)
+        CU(cudaMemcpyAsync(s.flags_host + (size_t)flag_block * FLAG_WORDS, flags, FLAG_WORDS * 4, cudaMemcpyDeviceToHost, st));
     return FOCR_OK;
 }
 
-// after the stream has been synchronised: did the chunk's hit list overflow?
 // after the stream has been synchronised: did a wait inside the tcgen05 kernel give up (protocol bug)?
-static int chunk_watchdog(Slot &s)
+static int chunk_watchdog(const unsigned int *fh)
 {
-    if (!s.flags_host[4]) return FOCR_OK;
-    return fail(FOCR_ERR_CUDA, "internal: scan_tc pipeline stalled (wait tag " + std::to_string(s.flags_host[5]) + ", info " +
-                                   std::to_string(s.flags_host[6]) + ", CTA " + std::to_string(s.flags_host[7]) + ", warp " +
-                                   std::to_string(s.flags_host[8]) + ", parity " + std::to_string(s.flags_host[9]) + ")");
+    if (!fh[4]) return FOCR_OK;
+    return fail(FOCR_ERR_CUDA, "internal: scan_tc pipeline stalled (wait tag " + std::to_string(fh[5]) + ", info " +
+                                   std::to_string(fh[6]) + ", CTA " + std::to_string(fh[7]) + ", warp " +
+                                   std::to_string(fh[8]) + ", parity " + std::to_string(fh[9]) + ")");
 }
 
-static bool chunk_overflowed(focr_ctx *c, Slot &s, uint32_t nB)
+// after the stream has been synchronised: did the chunk's candidate lists or its hit list overflow?  (grows the context's
+// capacities; the caller then repeats the scan)
+static bool chunk_overflowed(focr_ctx *c, Slot &s, const unsigned int *fh, uint32_t nB)
 {
     if (getenv("FOCR_DEBUG_COUNTS"))
         fprintf(stderr, "[focr] chunk of %u pages: hits %u, longest overflowing candidate list %u (cap %u)\n", nB,
-                s.flags_host[0], s.flags_host[3], c->cand_per_warp);
-    if (s.flags_host[3] > c->cand_per_warp) {  // a warp's private candidate list overflowed
-        c->cand_per_warp = (uint32_t)std::min<size_t>((size_t)s.flags_host[3] + s.flags_host[3] / 2, 1u << 24);
+                fh[0], fh[3], c->cand_per_warp);
+    if (fh[3] > c->cand_per_warp) {  // a warp's private candidate list overflowed
+        c->cand_per_warp = (uint32_t)std::min<size_t>((size_t)fh[3] + fh[3] / 2, 1u << 24);
         return true;
     }
     const size_t cap = (size_t)s.hits_per_page * nB;
-    const size_t seen = s.flags_host[0];
+    const size_t seen = fh[0];
     if (seen > cap) {
         const size_t need = (seen + nB - 1) / nB;
         c->hits_per_page = (uint32_t)std::min<size_t>(need + need / 4 + 1024, 0x7FFFFFFFu);
@@ -640,23 +679,87 @@ extern "C" int focr_ncc_scan_device(focr_ctx *c, const focr_bank *b, const uint8
     Geometry g;
     int rc = make_geometry(r_w, r_h, n_out, g);
     if (rc) return rc;
+    // All chunks are enqueued back to back (they share one slot's scratch, the stream orders them); each reports through
+    // its own flag block and the host looks at the blocks ONCE, after the last chunk (every FLAG_BLOCKS chunks for very
+    // large batches).  Only an overflowing candidate / hit list makes the host grow the lists and repeat the scan.
     for (int attempt = 0; attempt < 6; attempt++) {
         const uint32_t B = pick_chunk(b, g, n_pages, c->hits_per_page);
+        Slot &s = c->slot[0];
+        s.reserve_pages = B;
         bool redo = false;
-        for (uint32_t p0 = 0; p0 < n_pages && !redo; p0 += B) {
-            const uint32_t nB = std::min(B, n_pages - p0);
-            Slot &s = c->slot[0];
-            rc = enqueue_chunk(c, b, s, g, pages_dev + (size_t)p0 * page_stride, page_stride, pitch, nB, threshold, 1,
-                               out_dev + (size_t)p0 * b->T * n_out, counts_dev + (size_t)p0 * b->T);
-            if (rc) return rc;
+        for (uint32_t r0 = 0; r0 < n_pages && !redo; r0 += B * FLAG_BLOCKS) {
+            const uint32_t r1 = (uint32_t)std::min<uint64_t>((uint64_t)r0 + (uint64_t)B * FLAG_BLOCKS, n_pages);
+            int k = 0;
+            for (uint32_t p0 = r0; p0 < r1; p0 += B, k++) {
+                const uint32_t nB = std::min(B, r1 - p0);
+                rc = enqueue_chunk(c, b, s, g, pages_dev + (size_t)p0 * page_stride, page_stride, pitch, nB, threshold, 1,
+                                   out_dev + (size_t)p0 * b->T * n_out, counts_dev + (size_t)p0 * b->T, k, false);
+                if (rc) return rc;
+            }
+            CU(cudaMemcpyAsync(s.flags_host, s.flags.p, (size_t)k * FLAG_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
-            if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
-            if (int wrc = chunk_watchdog(s)) return wrc;
-            redo = chunk_overflowed(c, s, nB);
+            k = 0;
+            for (uint32_t p0 = r0; p0 < r1 && !redo; p0 += B, k++) {
+                const unsigned int *fh = s.flags_host + (size_t)k * FLAG_WORDS;
+                if (fh[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+                if (int wrc = chunk_watchdog(fh)) return wrc;
+                redo = chunk_overflowed(c, s, fh, std::min(B, r1 - p0));
+            }
         }
         if (!redo) return FOCR_OK;
     }
     return fail(FOCR_ERR_NOMEM, "hit list kept overflowing");
+}
+
+// ---- pageable callers: staged through library-owned pinned buffers with a few host threads
+static bool host_ptr_is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int stage_threads()
+{
+    static const int n = [] {
+        if (const char *e = getenv("FOCR_STAGE_THREADS")) return std::max(1, std::min(16, atoi(e)));
+        const unsigned hc = std::thread::hardware_concurrency();
+        return (int)std::max(1u, std::min(4u, hc / 2));
+    }();
+    return n;
+}
+
+// rows x row_bytes from src (stride src_stride) to dst (stride dst_stride), split over the staging threads
+static void parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows)
+{
+    if (rows == 1 || (dst_stride == row_bytes && src_stride == row_bytes)) {   // one contiguous block: split by bytes
+        const size_t total = row_bytes * rows;
+        const int nt = (int)std::max<size_t>(1, std::min<size_t>(stage_threads(), total >> 20));
+        if (nt == 1) {
+            memcpy(dst, src, total);
+            return;
+        }
+        std::vector<std::thread> th;
+        const size_t per = ((total + nt - 1) / nt + 4095) & ~(size_t)4095;
+        for (int i = 1; i < nt; i++) {
+            const size_t o = std::min(total, per * i), n = std::min(total, per * (i + 1)) - o;
+            if (n) th.emplace_back([=] { memcpy(dst + o, src + o, n); });
+        }
+        memcpy(dst, src, std::min(total, per));
+        for (auto &t : th) t.join();
+        return;
+    }
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(stage_threads(), rows));
+    std::vector<std::thread> th;
+    auto work = [=](int i) {
+        for (size_t r = i; r < rows; r += nt) memcpy(dst + r * dst_stride, src + r * src_stride, row_bytes);
+    };
+    for (int i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto &t : th) t.join();
 }
 
 static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_host, size_t page_stride,
@@ -669,6 +772,11 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
     if (rc) return rc;
     const size_t page_bytes = (size_t)r_w * r_h;
     const uint32_t T = b->T;
+    // Caller-owned buffers may be pageable (the reference hands over a Vec<u8>, ncc.rs:575): cudaMemcpyAsync would then
+    // stage through the driver's small bounce buffer synchronously.  Such buffers go through the slot's own pinned
+    // staging instead, filled / drained by a few host threads while the previous chunk computes.
+    const bool stage_in = !host_ptr_is_pinned(pages_host) || getenv("FOCR_FORCE_STAGING");
+    const bool stage_out = !host_ptr_is_pinned(out_host) || !host_ptr_is_pinned(counts_host) || getenv("FOCR_FORCE_STAGING");
     for (int attempt = 0; attempt < 6; attempt++) {
         const uint32_t B = pick_chunk(b, g, n_pages, c->hits_per_page);
         // chunk schedule {first page, pages}: the first chunks ramp up 2, 4, 8, .. B so that the kernels start after the
@@ -680,6 +788,25 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             p0 += nB;
         }
         bool redo = false;
+        const uint32_t Bres = std::min(B, n_pages);
+        for (auto &sl : c->slot) sl.reserve_pages = Bres;
+        // a chunk whose D2H has completed: check its flags, hand staged results to the caller
+        auto drain = [&](uint32_t k) -> int {
+            Slot &s = c->slot[k & 1];
+            const uint32_t p0 = chunks[k].first, nB = chunks[k].second;
+            if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
+            if (int wrc = chunk_watchdog(s.flags_host)) return wrc;
+            if (chunk_overflowed(c, s, s.flags_host, nB)) {
+                redo = true;
+                return FOCR_OK;
+            }
+            if (stage_out) {
+                parallel_copy((uint8_t *)(out_host + (size_t)p0 * T * n_out), 0, s.out_pin.as<uint8_t>(), 0,
+                              (size_t)nB * T * n_out * sizeof(focr_match), 1);
+                memcpy(counts_host + (size_t)p0 * T, s.counts_pin.p, (size_t)nB * T * 4);
+            }
+            return FOCR_OK;
+        };
         uint32_t ci = 0;
         // software pipeline over chunks: H2D of chunk i+1 overlaps the kernels of chunk i,
         // D2H of chunk i overlaps the kernels of chunk i+1
@@ -688,22 +815,24 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             Slot &s = c->slot[ci & 1];
             if (ci >= 2) {  // the slot's previous chunk must be fully drained before its buffers are reused
                 CU(cudaEventSynchronize(s.ev_d2h));
-                if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
-            if (int wrc = chunk_watchdog(s)) return wrc;
-                if (chunk_overflowed(c, s, chunks[ci - 2].second)) {
-                    redo = true;
-                    break;
-                }
+                if (int drc = drain(ci - 2)) return drc;
+                if (redo) break;
             }
-            CU(s.gray.ensure(page_bytes * nB));
-            CU(s.out.ensure((size_t)nB * T * n_out * sizeof(focr_match)));
-            CU(s.counts.ensure((size_t)nB * T * 4));
-            if (page_stride == page_bytes) {
-                CU(cudaMemcpyAsync(s.gray.p, pages_host + (size_t)p0 * page_stride, page_bytes * nB,
-                                   cudaMemcpyHostToDevice, c->h2d));
+            CU(s.gray.ensure(page_bytes * Bres));
+            CU(s.out.ensure((size_t)Bres * T * n_out * sizeof(focr_match)));
+            CU(s.counts.ensure((size_t)Bres * T * 4));
+            const uint8_t *src = pages_host + (size_t)p0 * page_stride;
+            size_t src_stride = page_stride;
+            if (stage_in) {
+                CU(s.gray_pin.ensure(page_bytes * Bres));
+                parallel_copy(s.gray_pin.as<uint8_t>(), page_bytes, src, page_stride, page_bytes, nB);
+                src = s.gray_pin.as<uint8_t>();
+                src_stride = page_bytes;
+            }
+            if (src_stride == page_bytes) {
+                CU(cudaMemcpyAsync(s.gray.p, src, page_bytes * nB, cudaMemcpyHostToDevice, c->h2d));
             } else {
-                CU(cudaMemcpy2DAsync(s.gray.p, page_bytes, pages_host + (size_t)p0 * page_stride, page_stride,
-                                     page_bytes, nB, cudaMemcpyHostToDevice, c->h2d));
+                CU(cudaMemcpy2DAsync(s.gray.p, page_bytes, src, src_stride, page_bytes, nB, cudaMemcpyHostToDevice, c->h2d));
             }
             CU(cudaEventRecord(s.ev_h2d, c->h2d));
             CU(cudaStreamWaitEvent(c->stream, s.ev_h2d, 0));
@@ -712,10 +841,16 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             if (rc) return rc;
             CU(cudaEventRecord(s.ev_compute, c->stream));
             CU(cudaStreamWaitEvent(c->d2h, s.ev_compute, 0));
-            CU(cudaMemcpyAsync(out_host + (size_t)p0 * T * n_out, s.out.p, (size_t)nB * T * n_out * sizeof(focr_match),
-                               cudaMemcpyDeviceToHost, c->d2h));
-            CU(cudaMemcpyAsync(counts_host + (size_t)p0 * T, s.counts.p, (size_t)nB * T * 4, cudaMemcpyDeviceToHost,
-                               c->d2h));
+            focr_match *dst_out = out_host + (size_t)p0 * T * n_out;
+            uint32_t *dst_counts = counts_host + (size_t)p0 * T;
+            if (stage_out) {
+                CU(s.out_pin.ensure((size_t)Bres * T * n_out * sizeof(focr_match)));
+                CU(s.counts_pin.ensure((size_t)Bres * T * 4));
+                dst_out = s.out_pin.as<focr_match>();
+                dst_counts = s.counts_pin.as<uint32_t>();
+            }
+            CU(cudaMemcpyAsync(dst_out, s.out.p, (size_t)nB * T * n_out * sizeof(focr_match), cudaMemcpyDeviceToHost, c->d2h));
+            CU(cudaMemcpyAsync(dst_counts, s.counts.p, (size_t)nB * T * 4, cudaMemcpyDeviceToHost, c->d2h));
             CU(cudaEventRecord(s.ev_d2h, c->d2h));
         }
         CU(cudaStreamSynchronize(c->h2d));
@@ -724,12 +859,8 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
         if (!redo) {
             // the last (up to) two chunks have not been checked yet
             const uint32_t n_chunks = ci;
-            for (uint32_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks; k++) {
-                Slot &s = c->slot[k & 1];
-                if (s.flags_host[1]) return fail(FOCR_ERR_CUDA, "internal: selection list overflow");
-            if (int wrc = chunk_watchdog(s)) return wrc;
-                if (chunk_overflowed(c, s, chunks[k].second)) redo = true;
-            }
+            for (uint32_t k = (n_chunks >= 2 ? n_chunks - 2 : 0); k < n_chunks && !redo; k++)
+                if (int drc = drain(k)) return drc;
         }
         if (!redo) return FOCR_OK;
     }
@@ -917,6 +1048,17 @@ extern "C" int focr_ncc_numerators(focr_ctx *c, const focr_bank *b, uint32_t t, 
 // ------------------------------------------------------------------------------------------ compat shim
 static std::mutex g_shim_mu;
 static focr_ctx *g_shim_ctx = nullptr;
+// The reference calls the kernel once per (page, offset, letter) (ncc.rs:587-702): the same needle comes back for every
+// page.  The shim keeps the banks of the most recent needles (keyed by their bytes) so that a repeated needle costs no
+// operand upload; a 1-template bank is a few KB of device memory.
+struct ShimBank {
+    std::vector<uint8_t> key;   // n_w, n_h (little-endian u16 each) + tight pixels
+    focr_bank *bank;
+    uint64_t stamp;
+};
+static std::vector<ShimBank> g_shim_banks;
+static uint64_t g_shim_clock = 0;
+constexpr size_t SHIM_BANKS = 4096;   // covers config 5's 3040 templates
 
 static size_t shim_scan(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *needle_u8, size_t N, size_t n_w,
                         size_t n_h, float threshold, focr_match *out, size_t n_out)
@@ -931,20 +1073,42 @@ static size_t shim_scan(uint8_t *reference, size_t r_w, size_t r_h, uint8_t *nee
         if (focr_ctx_create(dev ? atoi(dev) : 0, &g_shim_ctx) != FOCR_OK) die("focr_ctx_create");
     }
     if (n_out == 0 || n_w == 0 || n_h == 0 || n_w > N || r_w < n_w || r_h < n_h) return 0;
+    // "returns n_out when full" (ncc.cpp:225-227) cannot be honoured beyond the library's per-list capacity; the reference's
+    // callers use 1024 (ncc.rs:31,240).  Never return a truncated list as if it were complete.
+    if (n_out > 4096) {
+        fail(FOCR_ERR_UNSUPPORTED, "n_out = " + std::to_string(n_out) + " exceeds the supported 4096 matches per call");
+        die("ncc_*_u8");
+    }
     // unpad the needle rows (the bank API takes the tight canvas of ncc.rs:640)
-    std::vector<uint8_t> tight(n_w * n_h);
-    for (size_t y = 0; y < n_h; y++) memcpy(&tight[y * n_w], needle_u8 + y * N, n_w);
-    uint64_t off = 0;
-    uint16_t w16 = (uint16_t)n_w, h16 = (uint16_t)n_h;
+    std::vector<uint8_t> key(4 + n_w * n_h);
+    key[0] = (uint8_t)n_w, key[1] = (uint8_t)(n_w >> 8), key[2] = (uint8_t)n_h, key[3] = (uint8_t)(n_h >> 8);
+    for (size_t y = 0; y < n_h; y++) memcpy(&key[4 + y * n_w], needle_u8 + y * N, n_w);
     focr_bank *bank = nullptr;
-    if (focr_bank_create(g_shim_ctx, tight.data(), &off, &w16, &h16, 1, &bank) != FOCR_OK) die("focr_bank_create");
-    // n_out may exceed what one sort can hold; the reference's callers use 1024 (ncc.rs:31,240)
-    const uint32_t n_out32 = (uint32_t)std::min<size_t>(n_out, 4096);
+    for (auto &e : g_shim_banks)
+        if (e.key == key) {
+            bank = e.bank;
+            e.stamp = ++g_shim_clock;
+            break;
+        }
+    if (!bank) {
+        uint64_t off = 0;
+        uint16_t w16 = (uint16_t)n_w, h16 = (uint16_t)n_h;
+        if (focr_bank_create(g_shim_ctx, key.data() + 4, &off, &w16, &h16, 1, &bank) != FOCR_OK) die("focr_bank_create");
+        if (g_shim_banks.size() >= SHIM_BANKS) {   // evict the least recently used
+            size_t lru = 0;
+            for (size_t i = 1; i < g_shim_banks.size(); i++)
+                if (g_shim_banks[i].stamp < g_shim_banks[lru].stamp) lru = i;
+            focr_bank_destroy(g_shim_banks[lru].bank);
+            g_shim_banks[lru] = ShimBank{std::move(key), bank, ++g_shim_clock};
+        } else {
+            g_shim_banks.push_back(ShimBank{std::move(key), bank, ++g_shim_clock});
+        }
+    }
+    const uint32_t n_out32 = (uint32_t)n_out;
     std::vector<focr_match> tmp(n_out32);
     uint32_t cnt = 0;
     int rc = scan_host_impl(g_shim_ctx, bank, reference, r_w * r_h, (uint32_t)r_w, (uint32_t)r_h, 1, threshold, n_out32,
                             0 /* already inverted */, tmp.data(), &cnt);
-    focr_bank_destroy(bank);
     if (rc != FOCR_OK) die("scan");
     memcpy(out, tmp.data(), cnt * sizeof(focr_match));
     return cnt;

@@ -269,6 +269,12 @@ extern "C" int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size
     for (size_t i = 0; i < (size_t)n_glyphs * 64; i++)
         if (rasters[i].offset + (size_t)rasters[i].w * rasters[i].h > n_pixel_bytes)
             return focr_internal_fail(FOCR_ERR_ARG, "focr_glyph_bank_create: raster outside the pixel buffer");
+    // the kernel accumulates Sum g*(g - 2*ref) in 32-bit integers (the reference's sum_of_squares is i64, main.rs:510-516):
+    // |term| <= 255*255 per pixel, so a bitmap must stay below 2^31 / 65025 = 33025 pixels (a ~180 px glyph)
+    for (size_t i = 0; i < (size_t)n_glyphs * 64; i++)
+        if ((uint64_t)rasters[i].w * rasters[i].h * 65025ull >= (1ull << 31))
+            return focr_internal_fail(FOCR_ERR_UNSUPPORTED, "focr_glyph_bank_create: glyph bitmap of " + std::to_string(rasters[i].w) +
+                                                                "x" + std::to_string(rasters[i].h) + " pixels would overflow the 32-bit score");
     FCU(cudaSetDevice(focr_internal_device(ctx)));
     focr_glyph_bank *b = new focr_glyph_bank();
     b->ctx = ctx;

@@ -204,13 +204,11 @@ cudaError_t launch_stage_invert(const uint8_t *src, size_t src_page_stride, size
 
 cudaError_t launch_window_stats(const StatsArgs &a, int n_pages, cudaStream_t st)
 {
-    static bool attr_set = false;
     const size_t smem = window_stats_smem(std::max(a.n_w, a.n_w2), a.n_h);
-    if (!attr_set) {
+    {   // the opt-in is per DEVICE (a process may hold contexts on several GPUs): set it on every launch, it is cheap
         cudaError_t e = cudaFuncSetAttribute(window_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)window_stats_smem(MAX_TPL_W, MAX_TPL_H));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int xs = a.r_w - std::min(a.n_w, a.n_w2 ? a.n_w2 : a.n_w) + 1, ys = a.r_h - a.n_h + 1;
     dim3 grid((xs + ST_TW - 1) / ST_TW, (ys + ST_TH - 1) / ST_TH, n_pages);

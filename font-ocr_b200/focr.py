@@ -13,10 +13,12 @@ from .raster import FOCR_DEFAULT_ALPHABET, Font, f32
 
 
 class GlyphBank:
-    """focr_glyph_bank: 64 horizontal 26.6 phases of every alphabet glyph + f32 advances."""
+    """focr_glyph_bank: 64 horizontal 26.6 phases of every alphabet glyph + f32 advances.
+    `ctx` is an ncc.Context (one GPU) or an ncc.MultiContext (the bank is replicated to every device)."""
 
     def __init__(self, ctx, font: Font, size: float, alphabet: str = FOCR_DEFAULT_ALPHABET, kern_x: float = 1.0):
         self.ctx, self.font, self.alphabet, self.size = ctx, font, alphabet, size
+        self.multi = hasattr(ctx, "page_block")
         gids = [font.glyph_for_char(c) for c in alphabet]                       # main.rs:125-128
         x0 = y0 = 0                                                             # RectF::default() seeds the union
         for gid in gids:                                                        # main.rs:133-146
@@ -38,12 +40,13 @@ class GlyphBank:
                     off += bmp.size
         pixels = np.concatenate(chunks) if chunks else np.zeros(1, np.uint8)
         self._h = C.c_void_p()
-        check(lib().focr_glyph_bank_create(ctx._h, ptr(pixels), pixels.size, ptr(rasters), ptr(self.advance_px),
-                                           len(gids), int(self.origin[0]), C.byref(self._h)))
+        create = lib().focr_multi_glyph_bank_create if self.multi else lib().focr_glyph_bank_create
+        check(create(ctx._h, ptr(pixels), pixels.size, ptr(rasters), ptr(self.advance_px),
+                     len(gids), int(self.origin[0]), C.byref(self._h)))
 
     def close(self):
         if self._h:
-            lib().focr_glyph_bank_destroy(self._h)
+            (lib().focr_multi_glyph_bank_destroy if self.multi else lib().focr_glyph_bank_destroy)(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -65,9 +68,10 @@ def decode_images(ctx, bank: GlyphBank, pages: np.ndarray, x_start: int, y_start
     n_cells = np.zeros((P, max_lines), np.uint32)
     line_y = np.zeros((P, max_lines), np.uint32)
     n_lines = np.zeros(P, np.uint32)
-    check(lib().focr_decode_pages(ctx._h, bank._h, ptr(pages), r_w * r_h, r_w, r_h, P, x_start, y_start, width,
-                                  line_height, line_advance, max_lines, max_cells, ptr(glyphs), ptr(n_cells),
-                                  ptr(line_y), ptr(n_lines)))
+    decode = lib().focr_multi_decode_pages if bank.multi else lib().focr_decode_pages   # pages sharded over the GPUs
+    check(decode(ctx._h, bank._h, ptr(pages), r_w * r_h, r_w, r_h, P, x_start, y_start, width,
+                 line_height, line_advance, max_lines, max_cells, ptr(glyphs), ptr(n_cells),
+                 ptr(line_y), ptr(n_lines)))
     out = []
     for p in range(P):
         out.append([("".join(bank.alphabet[g] for g in glyphs[p, l, :n_cells[p, l]]), int(line_y[p, l]))

@@ -24,9 +24,12 @@ SYMBOLS = [
     "focr_ctx_create", "focr_ctx_destroy", "focr_ctx_set_kernel", "focr_ctx_stream", "focr_ctx_sync",
     "focr_ctx_launch_count", "focr_ctx_profile", "focr_ctx_profile_read",
     "focr_bank_create", "focr_bank_destroy", "focr_bank_size",
+    "focr_multi_create", "focr_multi_destroy", "focr_multi_size", "focr_multi_ctx", "focr_multi_page_block",
+    "focr_multi_bank_create", "focr_multi_bank_destroy", "focr_multi_ncc_scan",
+    "focr_multi_glyph_bank_create", "focr_multi_glyph_bank_destroy", "focr_multi_decode_pages",
     "focr_ncc_scan", "focr_ncc_scan_device", "focr_process_hits_device", "focr_window_stats", "focr_ncc_numerators",
     "focr_glyph_bank_create", "focr_glyph_bank_destroy", "focr_decode_pages", "focr_sum_of_squares",
-    "focr_host_process_hits", "focr_host_search_c_u8", "focr_bench_umma_i8", "focr_bench_umma_issue_cycles", "focr_bench_tmem", "focr_bench_pingpong",
+    "focr_host_process_hits", "focr_host_search_c_u8",
 ]
 
 
@@ -72,6 +75,23 @@ def lib():
     l.focr_bank_size.restype = u32
     l.focr_ncc_scan.argtypes = [vp, vp, vp, sz, u32, u32, u32, C.c_float, u32, vp, vp]
     l.focr_ncc_scan_device.argtypes = [vp, vp, vp, sz, sz, u32, u32, u32, C.c_float, u32, vp, vp]
+    l.focr_multi_create.argtypes = [vp, u32, C.POINTER(vp)]
+    l.focr_multi_destroy.argtypes = [vp]
+    l.focr_multi_destroy.restype = None
+    l.focr_multi_size.argtypes = [vp]
+    l.focr_multi_size.restype = u32
+    l.focr_multi_ctx.argtypes = [vp, u32]
+    l.focr_multi_ctx.restype = vp
+    l.focr_multi_page_block.argtypes = [vp, u32, u32, vp, vp]
+    l.focr_multi_page_block.restype = None
+    l.focr_multi_bank_create.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(vp)]
+    l.focr_multi_bank_destroy.argtypes = [vp]
+    l.focr_multi_bank_destroy.restype = None
+    l.focr_multi_ncc_scan.argtypes = [vp, vp, vp, sz, u32, u32, u32, C.c_float, u32, vp, vp]
+    l.focr_multi_glyph_bank_create.argtypes = [vp, vp, sz, vp, vp, u32, C.c_int32, C.POINTER(vp)]
+    l.focr_multi_glyph_bank_destroy.argtypes = [vp]
+    l.focr_multi_glyph_bank_destroy.restype = None
+    l.focr_multi_decode_pages.argtypes = [vp, vp, vp, sz] + [u32] * 10 + [vp, vp, vp, vp]
     l.focr_window_stats.argtypes = [vp, vp, u32, u32, u32, u32, vp, vp, vp]
     l.focr_ncc_numerators.argtypes = [vp, vp, u32, vp, u32, u32, vp]
     l.focr_glyph_bank_create.argtypes = [vp, vp, sz, vp, vp, u32, C.c_int32, C.POINTER(vp)]
@@ -80,10 +100,6 @@ def lib():
     l.focr_decode_pages.argtypes = [vp, vp, vp, sz] + [u32] * 10 + [vp, vp, vp, vp]
     l.focr_sum_of_squares.argtypes = [vp, vp, vp, sz, u32, vp]
     l.focr_process_hits_device.argtypes = [vp, vp, vp, u32, u32, u32, C.c_float, C.c_int32, u32, u32, vp, vp, vp, vp, vp, vp]
-    l.focr_bench_umma_i8.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
-    l.focr_bench_umma_issue_cycles.restype = C.c_double
-    l.focr_bench_pingpong.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
-    l.focr_bench_tmem.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
     l.focr_host_process_hits.argtypes = [vp, vp, vp, vp, u32, C.c_float, C.c_int32, vp, vp, vp]
     l.focr_host_search_c_u8.argtypes = [vp, u32, u32, vp, u32, u32, C.c_float, vp, vp]
     _lib = l

@@ -111,6 +111,92 @@ def scan_pages(ctx: Context, bank: Bank, pages: np.ndarray, threshold: float = 0
     return out, counts
 
 
+class MultiContext:
+    """focr_multi: one process, one context per GPU (the reference's page-parallel driver, ncc.rs:839-847)."""
+
+    def __init__(self, devices=None, n_devices: int = 0):
+        """devices: explicit list of device indices; else devices 0..n_devices-1 (0 = every visible device)."""
+        self._h = C.c_void_p()
+        if devices is not None:
+            arr = np.asarray(list(devices), np.int32)
+            check(lib().focr_multi_create(ptr(arr), len(arr), C.byref(self._h)))
+        else:
+            check(lib().focr_multi_create(None, n_devices, C.byref(self._h)))
+        self.size = int(lib().focr_multi_size(self._h))
+
+    def page_block(self, n_pages: int, i: int):
+        """(first page, pages) of device slot i for a batch of n_pages (== shard.shard_range)."""
+        a, b = np.zeros(1, np.uint32), np.zeros(1, np.uint32)
+        lib().focr_multi_page_block(self._h, n_pages, i, ptr(a), ptr(b))
+        return int(a[0]), int(b[0])
+
+    def sync(self):
+        for i in range(self.size):
+            check(lib().focr_ctx_sync(lib().focr_multi_ctx(self._h, i)))
+
+    def close(self):
+        if self._h:
+            lib().focr_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _pack_templates(templates):
+    tpls = [np.ascontiguousarray(t, np.uint8) for t in templates]
+    offsets = np.zeros(len(tpls), np.uint64)
+    o = 0
+    for i, t in enumerate(tpls):
+        offsets[i] = o
+        o += t.size
+    pixels = np.concatenate([t.ravel() for t in tpls]) if tpls else np.zeros(0, np.uint8)
+    n_w = np.array([t.shape[1] for t in tpls], np.uint16)
+    n_h = np.array([t.shape[0] for t in tpls], np.uint16)
+    return pixels, offsets, n_w, n_h
+
+
+class MultiBank:
+    """focr_multi_bank: the template bank replicated to every device of a MultiContext."""
+
+    def __init__(self, mctx: MultiContext, templates):
+        self.mctx = mctx
+        pixels, offsets, n_w, n_h = _pack_templates(templates)
+        self.T = len(offsets)
+        self._h = C.c_void_p()
+        check(lib().focr_multi_bank_create(mctx._h, ptr(pixels), ptr(offsets), ptr(n_w), ptr(n_h), self.T, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().focr_multi_bank_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scan_pages_multi(mctx: MultiContext, bank: MultiBank, pages: np.ndarray, threshold: float = 0.8, n_out: int = MAX_MATCHES,
+                     out: np.ndarray | None = None, counts: np.ndarray | None = None):
+    """focr_multi_ncc_scan: ONE batch sharded by page over the devices of `mctx`; same result layout as scan_pages."""
+    pages = np.ascontiguousarray(pages, np.uint8)
+    if pages.ndim == 2:
+        pages = pages[None]
+    P, r_h, r_w = pages.shape
+    if out is None:
+        out = np.zeros((P, bank.T, n_out), MATCH_DTYPE)
+    if counts is None:
+        counts = np.zeros((P, bank.T), np.uint32)
+    check(lib().focr_multi_ncc_scan(mctx._h, bank._h, ptr(pages), r_w * r_h, r_w, r_h, P, C.c_float(threshold), n_out,
+                                    ptr(out), ptr(counts)))
+    return out, counts
+
+
 def scan_pages_device(ctx: Context, bank: Bank, pages_ptr: int, page_stride: int, pitch: int, r_w: int, r_h: int,
                       n_pages: int, threshold: float, n_out: int, out_ptr: int, counts_ptr: int):
     """focr_ncc_scan_device on raw device addresses (e.g. torch tensors' data_ptr())."""

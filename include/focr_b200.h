@@ -124,17 +124,44 @@ uint32_t focr_bank_size(const focr_bank *bank);
  * out_host[(p*T + t)*n_out + k] is the k-th hit of template t on page p in the reference's
  * emission order ((y, x) raster order, truncated at n_out exactly like ncc.cpp:225-227);
  * counts_host[p*T + t] is what search_c_u8 would have got back as n_matches (== n_out when full).
- * The timed end-to-end path: H2D of the pages, all kernels, D2H of the match lists. */
+ * The timed end-to-end path: H2D of the pages, all kernels, D2H of the match lists.
+ * The host buffers may be pageable (a Rust Vec<u8>, ncc.rs:575) or pinned: pageable ones are staged through
+ * pinned buffers the context owns (a few host threads copy while the previous chunk computes); pinned ones
+ * (cudaHostAlloc / cudaHostRegister) are used for the DMA directly. */
 int focr_ncc_scan(focr_ctx *ctx, const focr_bank *bank, const uint8_t *pages_host, size_t page_stride,
                   uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
                   focr_match *out_host, uint32_t *counts_host);
 
 /* Same scan with the pages already resident in device memory (gray, row pitch `pitch` bytes) and
- * the results left in device memory; asynchronous on focr_ctx_stream().  This is what bench.py
- * times as `value` (inputs in HBM when the timed region starts). */
+ * the results left in device memory.  All work is enqueued on focr_ctx_stream() back to back; the
+ * call then waits ONCE for the stream and checks the chunks' overflow flags (a candidate or hit list
+ * that overflowed grows and the scan is repeated), so the results are complete when it returns.
+ * This is what bench.py times as `value` (inputs in HBM when the timed region starts). */
 int focr_ncc_scan_device(focr_ctx *ctx, const focr_bank *bank, const uint8_t *pages_dev, size_t page_stride,
                          size_t pitch, uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold,
                          uint32_t n_out, focr_match *out_dev, uint32_t *counts_dev);
+
+/* ---- one process, several GPUs (csrc/multi.cpp): the reference's page-parallel driver, `pages.par_iter().map(..)`
+ * + `sort_by_key(page index)` (ncc.rs:839-847, main.rs:443-468).  A focr_multi owns one context per device; banks are
+ * replicated to every device once; a scan splits the batch into contiguous page blocks (sizes differ by at most one,
+ * lower devices first -- focr_multi_page_block reports them), every device runs its block through focr_ncc_scan /
+ * focr_decode_pages from its own host thread, and the results land at the block's place in the caller's arrays: the
+ * output is indexed by page exactly like the single-device call.  Nothing is exchanged between GPUs (no collective).
+ * devices == NULL: devices 0 .. n_devices-1, or every visible device when n_devices == 0.  On failure the message of the
+ * first failing device is left in focr_last_error(). */
+typedef struct focr_multi focr_multi;
+typedef struct focr_multi_bank focr_multi_bank;
+int focr_multi_create(const int *devices, uint32_t n_devices, focr_multi **out);
+void focr_multi_destroy(focr_multi *m);
+uint32_t focr_multi_size(const focr_multi *m);
+focr_ctx *focr_multi_ctx(focr_multi *m, uint32_t i);
+void focr_multi_page_block(const focr_multi *m, uint32_t n_pages, uint32_t i, uint32_t *first, uint32_t *count);
+int focr_multi_bank_create(focr_multi *m, const uint8_t *pixels, const uint64_t *offsets, const uint16_t *n_w,
+                           const uint16_t *n_h, uint32_t n_templates, focr_multi_bank **out);
+void focr_multi_bank_destroy(focr_multi_bank *bank);
+int focr_multi_ncc_scan(focr_multi *m, const focr_multi_bank *bank, const uint8_t *pages_host, size_t page_stride,
+                        uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
+                        focr_match *out_host, uint32_t *counts_host);
 
 /* Parity probes (tests/): the raw quantities north_star wants bit-exact.
  * window stats for one page and one box size: s_p[y*r_w+x], s2_p[y*r_w+x] for x<=r_w-n_w, y<=r_h-n_h
@@ -185,6 +212,18 @@ int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, const uint8_t 
                       uint32_t max_cells, uint16_t *glyphs_host, uint32_t *n_cells_host,
                       uint32_t *line_y_host, uint32_t *n_lines_host);
 
+/* focr on several GPUs: see focr_multi above (main.rs:443-468). */
+typedef struct focr_multi_glyph_bank focr_multi_glyph_bank;
+int focr_multi_glyph_bank_create(focr_multi *m, const uint8_t *pixels, size_t n_pixel_bytes,
+                                 const focr_glyph_raster *rasters, const float *advance_px, uint32_t n_glyphs,
+                                 int32_t origin_x, focr_multi_glyph_bank **out);
+void focr_multi_glyph_bank_destroy(focr_multi_glyph_bank *bank);
+int focr_multi_decode_pages(focr_multi *m, const focr_multi_glyph_bank *bank, const uint8_t *pages_host, size_t page_stride,
+                            uint32_t r_w, uint32_t r_h, uint32_t n_pages, uint32_t x_start, uint32_t y_start,
+                            uint32_t width, uint32_t line_height, uint32_t line_advance, uint32_t max_lines,
+                            uint32_t max_cells, uint16_t *glyphs_host, uint32_t *n_cells_host,
+                            uint32_t *line_y_host, uint32_t *n_lines_host);
+
 /* Device-side process_hits (ncc.rs:723-786 with partition_by, ncc.rs:1036-1052) for a batch of pages whose match
  * lists are still resident in HBM -- the out_dev / counts_dev buffers focr_ncc_scan_device filled (template order =
  * the reference's get_hits order, ncc.rs:675-681).  Anchor filter, the two stable sorts (as one radix sort by
@@ -206,24 +245,6 @@ int focr_process_hits_device(focr_ctx *ctx, const focr_match *matches_dev, const
  * decode kernel uses the algebraically identical Sum(ref^2) - 2*dot + Sum(g^2) form). */
 int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys_host, size_t len,
                         uint32_t n_pairs, int64_t *out_host);
-
-/* Measurement aid: tcgen05.mma kind::i8 micro-benchmark (csrc/umma_bench.cu).  Every SM issues
- * iters*ksteps MMAs of M=128, N=n, K=32 (u8 x u8 -> s32) into nacc rotating accumulators;
- * cycles_per_mma is the median over SMs.  bench.py --measure-int8 uses it for the roofline denominator
- * (MEASURED_PEAKS.json has no integer tensor peak). */
-int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
-                       double *ms_total);
-
-double focr_bench_umma_issue_cycles(void);
-/* Measurement aid: cycles per hand-shake round trip "signal (tcgen05.commit or arrive) -> nwait warps wait and answer ->
- * the signaller waits" with the three ways of waiting on an mbarrier (0 try_wait + suspend hint, 1 try_wait, 2 test_wait). */
-int focr_bench_pingpong(focr_ctx *ctx, int wait_kind, int use_commit, int nwait, int iters, double *cycles_per_round);
-
-/* Measurement aid: TMEM <-> register traffic (tcgen05.ld / tcgen05.st 32x32b.x32) from nw warps, optionally
- * while another warp streams MMAs of N = mma_n; mode 0 = ld, 1 = ld + st, 2 = st, 3 = ld + the screen's max tree.
- * The correlation kernel's epilogue ceiling. */
-int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int mma_n, int mma_count, double *cycles_per_round,
-                    double *cycles_per_mma);
 
 /* ------------------------------------------------------------------------------------------
  * Section 4 -- C hooks into the C++ host mirror (font-ocr_b200/host/focr_host.hpp), used by tests.

@@ -63,6 +63,13 @@ def port_lib():
         lib.orc_image_to_u8.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.orc_sum_of_squares.restype = C.c_int64
         lib.orc_sum_of_squares.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.orc_decode_line_cached.restype = C.c_size_t
+        lib.orc_decode_line_cached.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.orc_decode_image_cached.restype = C.c_size_t
+        lib.orc_decode_image_cached.argtypes = [C.c_void_p] + [C.c_size_t] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                                                  C.c_size_t, C.c_size_t, C.c_void_p]
         _port = lib
     return _port
 
@@ -319,3 +326,56 @@ def decode_image(gray: np.ndarray, font, alphabet: str, size: float, x_start: in
         if max_lines is not None and len(out) >= max_lines:
             break
     return out
+
+
+# --------------------------------------------------------------------------- focr with cached glyph rasters
+RASTER_DTYPE = np.dtype([("offset", np.uint64), ("left", np.int16), ("top", np.int16), ("w", np.uint16), ("h", np.uint16)])
+
+
+class GlyphCache:
+    """The (glyph, 26.6 phase) raster cache BASELINE config 4 names, built with the same producer calls decode_line makes
+    per cell (main.rs:98-106): 64 horizontal phases per alphabet glyph, the vertical delta fixed by the origin
+    (main.rs:147), and the f32 advances of main.rs:176-178."""
+
+    def __init__(self, font, alphabet: str, size: float, kern_x: float = 1.0):
+        f32 = np.float32
+        self.alphabet = alphabet
+        gids = [font.glyph_for_char(c) for c in alphabet]                       # main.rs:125-128
+        x0 = y0 = 0                                                             # RectF::default()
+        for gid in gids:                                                        # main.rs:133-146
+            a, b, _c, _d = font.raster_bounds(gid, size, 0.0, 0.0)
+            x0, y0 = min(x0, a), min(y0, b)
+        self.origin_x, origin_y = -x0, -y0                                      # main.rs:147
+        upem = f32(font.units_per_em)
+        self.advance_px = np.array([f32(f32(f32(font.advance(g)[0] / upem) * f32(size)) * f32(kern_x)) for g in gids],
+                                   np.float32)
+        self.rasters = np.zeros((len(gids), 64), RASTER_DTYPE)
+        chunks, off = [], 0
+        for gi, gid in enumerate(gids):
+            for ph in range(64):
+                bmp, left, top = font.glyph_bitmap(gid, size, ph, -int(f32(f32(origin_y) * f32(64.0))))
+                h, w = bmp.shape if bmp.size else (0, 0)
+                self.rasters[gi, ph] = (off, left, -top, w, h)
+                if bmp.size:
+                    chunks.append(bmp.ravel())
+                    off += bmp.size
+        self.pixels = np.concatenate(chunks) if chunks else np.zeros(1, np.uint8)
+
+
+def decode_image_cached(gray: np.ndarray, cache: GlyphCache, x_start: int, y_start: int, width: int, line_height: int,
+                        line_advance: int, max_cells: int = 512):
+    """main.rs:183-218 with score_glyph's rasterisation served from `cache` (C restatement): [(text, y)]."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    H, W = gray.shape
+    max_lines = max((max(H - y_start, 0) + line_advance - 1) // line_advance, 1)
+    glyphs = np.zeros((max_lines, max_cells), np.uint16)
+    n_cells = np.zeros(max_lines, np.uint32)
+    line_y = np.zeros(max_lines, np.uint32)
+    scratch = np.zeros(2 * width * line_height + 64, np.uint8)
+    n = port_lib().orc_decode_image_cached(_p(gray), W, H, x_start, y_start, width, line_height, line_advance,
+                                           _p(cache.pixels), _p(cache.rasters), _p(cache.advance_px), len(cache.alphabet),
+                                           int(cache.origin_x), _p(glyphs), _p(n_cells), _p(line_y), max_lines, max_cells,
+                                           _p(scratch))
+    if n == 2 ** 64 - 1:
+        raise OverflowError("a line needs more than max_cells cells")
+    return [("".join(cache.alphabet[g] for g in glyphs[l, :n_cells[l]]), int(line_y[l])) for l in range(n)]

@@ -27,3 +27,19 @@ def test_oracle_decodes_rendered_line(oracle, font, pkg):
     # the greedy walk derails on a proportional face (README.md: only tested with a monospace font), but
     # it must at least lock on to the start of the line it was rendered from
     assert out[0][0][:4] == lines[0][:4]
+
+
+def test_cached_decode_equals_per_cell_rasterisation(oracle, font, pkg):
+    """BASELINE config 4 runs focr "with cached glyph rasters".  The cached C restatement (oracle.decode_image_cached:
+    the reference's whole-canvas sum_of_squares, rasters from a (glyph, 26.6 phase) cache) must decode exactly what the
+    per-cell restatement (oracle.decode_image: one rasterisation per glyph per cell like main.rs:98-106) decodes --
+    including a skipped all-white rectangle and a last rectangle clamped by crop_imm."""
+    alphabet = "> =ABCDEFGHabcdefgh0123+/"
+    H = 39 + 15 * 3 + 7
+    page = pkg.pages.make_focr_page(font, 13, 400, H, seed=4, line_width=300, fill=1.0)[0]
+    page[39 + 15:39 + 15 + 12, :] = 255     # an all-white rectangle: skipped (main.rs:208-211)
+    page[H - 6:H - 2, 60:200] = 0           # ink inside the clamped last strip
+    cache = oracle.GlyphCache(font, alphabet, 13)
+    got = oracle.decode_image_cached(page, cache, 45, 39, 300, 12, 15)
+    exp = oracle.decode_image(page, font, alphabet, 13, 45, 39, 300, 12, 15)
+    assert got == exp and len(got) >= 2 and got[-1][1] == 39 + 15 * 3

@@ -50,3 +50,30 @@ def test_decode_batch_and_clamped_last_strip(ctx, oracle, font, pkg):
         exp = oracle.decode_image(pages[p], font, alphabet, 13, 45, 39, 300, 12, 15)
         assert got[p] == exp
     bank.close()
+
+
+def test_config4_full_page_and_multi_device(ctx, oracle, font, pkg):
+    """BASELINE config 4 at its named shape: -x 45 -y 39 -w 608 --line-height 12 --line-advance 15 on full 2480x3508 pages
+    with the cached glyph rasters, against the cached C restatement (pinned to the per-cell restatement in
+    tests/test_focr_oracle.py); then the same batch sharded by page over a focr_multi (every visible GPU, or two contexts
+    on device 0) must give the same lines."""
+    import torch
+    from font_ocr_b200 import focr, ncc
+
+    alphabet = pkg.raster.FOCR_DEFAULT_ALPHABET
+    pages = np.stack([pkg.pages.make_focr_page(font, 13, 2480, 3508, seed=7100 + i)[0] for i in range(3)])
+    bank = focr.GlyphBank(ctx, font, 13, alphabet)
+    got = focr.decode_images(ctx, bank, pages, 45, 39, 608, 12, 15)
+    bank.close()
+    cache = oracle.GlyphCache(font, alphabet, 13)
+    exp0 = oracle.decode_image_cached(pages[0], cache, 45, 39, 608, 12, 15)
+    assert got[0] == exp0 and len(exp0) > 200
+    n_gpu = torch.cuda.device_count()
+    mctx = ncc.MultiContext(devices=list(range(n_gpu)) if n_gpu > 1 else [0, 0])
+    try:
+        mbank = focr.GlyphBank(mctx, font, 13, alphabet)
+        got_m = focr.decode_images(mctx, mbank, pages, 45, 39, 608, 12, 15)
+        mbank.close()
+    finally:
+        mctx.close()
+    assert got_m == got

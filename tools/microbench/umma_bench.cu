@@ -1,4 +1,5 @@
-// umma_bench.cu -- tcgen05.mma kind::i8 micro-benchmark (measurement aid, not on the product path).
+// umma_bench.cu -- tcgen05 micro-benchmarks (measurement aids; built into tools/microbench/libfocr_microbench.so,
+// NOT part of libfocr_b200.so or its header).
 //
 // MEASURED_PEAKS.json has no integer tensor peak, and the correlation kernel's design hinges on how
 // long ONE tcgen05.mma of a given N takes (scan_tc.cu issues many small ones).  Every SM runs one CTA
@@ -9,11 +10,19 @@
 #include <string>
 #include <vector>
 
-#include "common.cuh"
+#include <cuda_runtime.h>
 
-int focr_internal_fail(int code, const std::string &msg);
-int focr_internal_device(const focr_ctx *ctx);
-extern "C" void *focr_ctx_stream(focr_ctx *ctx);
+#include "focr_microbench.h"
+
+// measurement aids live outside the product library (libfocr_b200.so) and its header; they only share the error codes
+enum { FOCR_OK = 0, FOCR_ERR_CUDA = 1, FOCR_ERR_ARG = 2 };
+static thread_local std::string g_mb_err;
+static int focr_internal_fail(int code, const std::string &msg)
+{
+    g_mb_err = msg;
+    return code;
+}
+extern "C" const char *focr_microbench_last_error(void) { return g_mb_err.c_str(); }
 
 namespace focr {
 
@@ -271,17 +280,17 @@ static double g_last_issue_cycles = 0;
 extern "C" double focr_bench_umma_issue_cycles(void) { return g_last_issue_cycles; }
 
 // n: MMA N (multiple of 16, <= 256); returns the median over SMs of cycles per tcgen05.mma and the wall time
-extern "C" int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
+extern "C" int focr_bench_umma_i8(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
                                   double *ms_total)
 {
     using namespace focr;
-    if (!ctx || !cycles_per_mma || !ms_total || n < 16 || n > 256 || (n & 15) || ksteps < 1 || ksteps > 16 || iters < 1 ||
+    if (device < 0 || !cycles_per_mma || !ms_total || n < 16 || n > 256 || (n & 15) || ksteps < 1 || ksteps > 16 || iters < 1 ||
         nacc < 1 || nacc * ((n + 31) & ~31) > 512)
         return focr_internal_fail(FOCR_ERR_ARG, "focr_bench_umma_i8: bad argument");
-    if (cudaSetDevice(focr_internal_device(ctx)) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
-    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    if (cudaSetDevice(device) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
+    cudaStream_t st = nullptr;
     int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     long long *d = nullptr;
     if (cudaMalloc((void **)&d, sms * 16) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
     const size_t smem = (size_t)ksteps * 2 * (128 + n) * 16 + 1024;
@@ -313,17 +322,17 @@ extern "C" int focr_bench_umma_i8(focr_ctx *ctx, int n, int ksteps, int iters, i
 
 // TMEM load/store micro-benchmark (see tmem_bench_kernel): cycles per 32x32b.x32 round per warp (median over SMs of the
 // slowest warp) and cycles per MMA of the concurrent tensor-core stream (0 when mma_n == 0).
-extern "C" int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int mma_n, int mma_count, double *cycles_per_round,
+extern "C" int focr_bench_tmem(int device, int nw, int mode, int iters, int mma_n, int mma_count, double *cycles_per_round,
                                double *cycles_per_mma)
 {
     using namespace focr;
-    if (!ctx || !cycles_per_round || !cycles_per_mma || nw < 4 || nw > 16 || (nw & 3) || mode < 0 || mode > 3 || iters < 1 ||
+    if (device < 0 || !cycles_per_round || !cycles_per_mma || nw < 4 || nw > 16 || (nw & 3) || mode < 0 || mode > 3 || iters < 1 ||
         mma_n < 0 || mma_n > 256 || (mma_n & 15))
         return focr_internal_fail(FOCR_ERR_ARG, "focr_bench_tmem: bad argument");
-    if (cudaSetDevice(focr_internal_device(ctx)) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
-    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    if (cudaSetDevice(device) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
+    cudaStream_t st = nullptr;
     int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     long long *d = nullptr;
     if (cudaMalloc((void **)&d, sms * 16) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
     const size_t smem = (size_t)7 * 2 * (128 + 256) * 16 + 1024;
@@ -345,15 +354,15 @@ extern "C" int focr_bench_tmem(focr_ctx *ctx, int nw, int mode, int iters, int m
 }
 
 // cycles per hand-shake round trip (see pingpong_kernel), median over SMs
-extern "C" int focr_bench_pingpong(focr_ctx *ctx, int wait_kind, int use_commit, int nwait, int iters, double *cycles_per_round)
+extern "C" int focr_bench_pingpong(int device, int wait_kind, int use_commit, int nwait, int iters, double *cycles_per_round)
 {
     using namespace focr;
-    if (!ctx || !cycles_per_round || wait_kind < 0 || wait_kind > 2 || nwait < 1 || nwait > 8 || iters < 1)
+    if (device < 0 || !cycles_per_round || wait_kind < 0 || wait_kind > 2 || nwait < 1 || nwait > 8 || iters < 1)
         return focr_internal_fail(FOCR_ERR_ARG, "focr_bench_pingpong: bad argument");
-    if (cudaSetDevice(focr_internal_device(ctx)) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
-    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    if (cudaSetDevice(device) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaSetDevice");
+    cudaStream_t st = nullptr;
     int sms = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, focr_internal_device(ctx));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     long long *d = nullptr;
     if (cudaMalloc((void **)&d, sms * 8) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
     pingpong_kernel<<<sms, 32 * 9, 0, st>>>(wait_kind, use_commit, nwait, iters, d);
