@@ -154,6 +154,11 @@ struct StageTimer {  // RAII: events around one stage when profiling is on
     }
 };
 
+void focr_internal_streams(focr_ctx *c, cudaStream_t out[3]) { out[0] = c->stream, out[1] = c->h2d, out[2] = c->d2h; }
+// focr_decode.cu times its kernel through these (the StageTimer lives here)
+void *focr_internal_stage_begin(focr_ctx *c, int stage) { return new StageTimer(c, stage); }
+void focr_internal_stage_end(void *t) { delete (StageTimer *)t; }
+
 struct ExactStage : TcHook {  // the exact pass as its own profiling stage (inside FOCR_STAGE_SCAN)
     focr_ctx *c; StageTimer *t = nullptr;
     explicit ExactStage(focr_ctx *c_) : c(c_) {}
@@ -712,6 +717,8 @@ extern "C" int focr_ncc_scan_device(focr_ctx *c, const focr_bank *b, const uint8
 }
 
 // ---- pageable callers: staged through library-owned pinned buffers with a few host threads
+bool focr_internal_host_pinned(const void *p);
+void focr_internal_parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows);
 static bool host_ptr_is_pinned(const void *p)
 {
     cudaPointerAttributes at;
@@ -760,6 +767,12 @@ static void parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, s
     for (int i = 1; i < nt; i++) th.emplace_back(work, i);
     work(0);
     for (auto &t : th) t.join();
+}
+
+bool focr_internal_host_pinned(const void *p) { return host_ptr_is_pinned(p); }
+void focr_internal_parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows)
+{
+    parallel_copy(dst, dst_stride, src, src_stride, row_bytes, rows);
 }
 
 static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_host, size_t page_stride,

@@ -34,6 +34,11 @@ struct GlyphBankDev {
     // {byte offset of the row in `pixels`, glyph | w << 16, (u16)left | (u16)(top + row) << 16, 0}
     const uint4 *tasks;                // [task_off[64]]
     const uint32_t *task_off;          // [65]
+    // dense tiles (the fast path): for every phase and glyph the bitmap drawn on a tile_rows x tile_wb byte tile whose
+    // top-left corner sits at canvas position (dint + tile_left, 0): [64][n_glyphs][tile_rows][tile_wb], zero filled.
+    // Rows above the canvas (never visible, Canvas::blit_from clips them) are dropped.  nullptr: bitmaps too large.
+    const uint8_t *tiles;
+    int tile_rows, tile_wb, tile_left;
 };
 
 constexpr uint32_t FD_MAX_SCORES = 256;   // glyphs per bank the row-task path keeps scores for (per warp, shared memory)
@@ -212,6 +217,155 @@ __global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_kernel(DecodeArgs a
     if (lane == 0) *n_cells_out = n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The fast path: every cell is a small integer GEMV.  For the cell's 26.6 phase the bank holds one dense
+// tile_rows x tile_wb byte tile per glyph (zeros around the bitmap), all on the same canvas grid; the strip bytes under
+// that grid -- the WINDOW, tile_wb columns from canvas column dint + tile_left -- are aligned once per cell into shared
+// memory and then every lane scores its glyphs against it:  Sum g*g - 2 * Sum g*ref  with two __dp4a per 4 pixels, one
+// 16-byte bank load and one 16-byte (broadcast) window load per 16 pixels.  Same integers as the reference's
+// sum_of_squares over the whole canvas minus the glyph-independent Sum ref^2: the strip is zero padded on
+// both sides so that pixels outside the canvas add nothing to Sum g*ref, and in the cells whose window crosses the
+// canvas edge Sum g*g only counts the columns inside (Canvas::blit_from clips the bitmap, main.rs:98-106).
+constexpr int FD_PAD = 64;   // zero columns on either side of a staged strip (>= tile_wb + |origin + tile_left|, checked on the host)
+
+template <int WORDS>   // 16-byte groups per tile row: tile_wb = 16 * WORDS
+__global__ void __launch_bounds__(FD_WARPS * 32) focr_decode_tile_kernel(DecodeArgs a)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t line = blockIdx.x * FD_WARPS + warp;
+    const uint32_t page = blockIdx.y;
+    if (line >= a.max_lines) return;
+    uint32_t *n_cells_out = a.n_cells + (size_t)page * a.max_lines + line;
+    // crop_imm clamps the rectangle to the image (main.rs:201-203)
+    const uint32_t y0 = a.y_start + line * a.line_advance;
+    const uint32_t xs = min(a.x_start, a.r_w), ys = min(y0, a.r_h);
+    const uint32_t w = min(a.width, a.r_w - xs), h = min(a.line_height, a.r_h - ys);
+    if (h == 0 || w == 0) {  // height 0 ends the page (main.rs:205-207); width 0 is an all-white strip
+        if (lane == 0) *n_cells_out = 0xFFFFFFFFu;
+        return;
+    }
+    // per warp: the inverted strip with FD_PAD zero columns on both sides (row pitch sp, a multiple of 4), then the window
+    const int sp = (int)((a.width + 2 * FD_PAD + 3) & ~3u);
+    const int R = a.bank.tile_rows, WB = 16 * WORDS;
+    const size_t strip_bytes = ((size_t)sp * a.line_height + 16 + 15) & ~(size_t)15;   // + 16: the word loads may run past the last row
+    uint8_t *strip = smem + (size_t)warp * (strip_bytes + (size_t)R * WB);
+    uint4 *win = (uint4 *)(strip + strip_bytes);
+    {
+        uint32_t *z = (uint32_t *)strip;
+        for (int i = lane; i < (int)(strip_bytes / 4); i += 32) z[i] = 0u;
+    }
+    __syncwarp();
+    const uint8_t *src = a.pages + (size_t)page * a.page_stride + (size_t)ys * a.r_w + xs;
+    uint32_t any_ink = 0;
+    for (uint32_t i = lane; i < w * h; i += 32) {
+        const uint32_t r = i / w, c = i - r * w;
+        const uint8_t v = 255 - src[(size_t)r * a.r_w + c];   // main.rs:150
+        strip[r * sp + FD_PAD + c] = v;
+        any_ink |= v;
+    }
+    any_ink = __reduce_or_sync(0xffffffffu, any_ink);
+    __syncwarp();
+    if (any_ink == 0) {  // all pixels == 255: skipped (main.rs:208-211)
+        if (lane == 0) *n_cells_out = 0xFFFFFFFFu;
+        return;
+    }
+    uint16_t *out = a.glyphs + ((size_t)page * a.max_lines + line) * a.max_cells;
+    const int rows = min((int)h, R);            // tile rows on the canvas (a clamped last strip has fewer)
+    const int n_glyphs = (int)a.bank.n_glyphs;
+    const size_t glyph_stride = (size_t)R * WORDS;                 // uint4 per glyph tile
+    float pos = 0.f;  // Vector2F pen, x component (main.rs:123)
+    uint32_t n = 0;
+    const float wf = (float)w;
+    while (pos < wf) {  // main.rs:158
+        // font-kit: translation -> 26.6 by `(x * 64.0) as i32` (truncation); translation = origin + pos
+        const float tx = __fadd_rn(a.origin_x, pos);
+        const int d26 = (int)__fmul_rn(tx, 64.0f);
+        const int dint = d26 >> 6, frac = d26 & 63;
+        const int x0 = dint + a.bank.tile_left;                    // canvas column of the tile's first column
+        // the window: rows x WB strip bytes from column x0, aligned into shared memory (one 4-byte word per lane and step)
+        {
+            const int nwords = rows * WORDS * 4;
+            for (int i = lane; i < nwords; i += 32) {
+                const int r = i / (WORDS * 4), q = i - r * (WORDS * 4);
+                const uintptr_t p = (uintptr_t)(strip + r * sp + FD_PAD + x0 + 4 * q);
+                const uint32_t *wp = (const uint32_t *)(p & ~(uintptr_t)3);
+                ((uint32_t *)win)[i] = __funnelshift_r(wp[0], wp[1], (int)(p & 3) * 8);
+            }
+        }
+        __syncwarp();
+        const bool edge = x0 < 0 || x0 + WB > (int)w;             // warp-uniform: some tile columns lie outside the canvas
+        uint32_t cmask[WORDS * 4];
+#pragma unroll
+        for (int q = 0; q < WORDS * 4; q++) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int cx = x0 + 4 * q + b;
+                if (cx >= 0 && cx < (int)w) m |= 0xFFu << (8 * b);
+            }
+            cmask[q] = m;
+        }
+        const uint4 *tile0 = (const uint4 *)a.bank.tiles + (size_t)frac * n_glyphs * glyph_stride;
+        int best_score = 0x7fffffff;
+        uint32_t best_g = 0xFFFFFFFFu;
+        for (int g = lane; g < n_glyphs; g += 32) {
+            const uint4 *tile = tile0 + (size_t)g * glyph_stride;
+            uint32_t g2 = 0, gr = 0;
+            if (!edge) {
+#pragma unroll 4
+                for (int r = 0; r < rows; r++) {
+#pragma unroll
+                    for (int k = 0; k < WORDS; k++) {
+                        const uint4 t = __ldg(tile + r * WORDS + k);
+                        const uint4 v = win[r * WORDS + k];
+                        g2 = __dp4a(t.x, t.x, g2), gr = __dp4a(t.x, v.x, gr);
+                        g2 = __dp4a(t.y, t.y, g2), gr = __dp4a(t.y, v.y, gr);
+                        g2 = __dp4a(t.z, t.z, g2), gr = __dp4a(t.z, v.z, gr);
+                        g2 = __dp4a(t.w, t.w, g2), gr = __dp4a(t.w, v.w, gr);
+                    }
+                }
+            } else {
+                for (int r = 0; r < rows; r++) {
+#pragma unroll
+                    for (int k = 0; k < WORDS; k++) {
+                        const uint4 t = __ldg(tile + r * WORDS + k);
+                        const uint4 v = win[r * WORDS + k];
+                        g2 = __dp4a(t.x & cmask[4 * k], t.x, g2), gr = __dp4a(t.x, v.x, gr);
+                        g2 = __dp4a(t.y & cmask[4 * k + 1], t.y, g2), gr = __dp4a(t.y, v.y, gr);
+                        g2 = __dp4a(t.z & cmask[4 * k + 2], t.z, g2), gr = __dp4a(t.z, v.z, gr);
+                        g2 = __dp4a(t.w & cmask[4 * k + 3], t.w, g2), gr = __dp4a(t.w, v.w, gr);
+                    }
+                }
+            }
+            const int score = (int)g2 - 2 * (int)gr;
+            if (score < best_score) {  // within a lane glyph indices ascend: strict < keeps the first minimum
+                best_score = score;
+                best_g = (uint32_t)g;
+            }
+        }
+        // warp argmin with the reference's tie-break: min_by_key returns the FIRST minimum (main.rs:159-172)
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const int os = __shfl_xor_sync(0xffffffffu, best_score, d);
+            const uint32_t og = __shfl_xor_sync(0xffffffffu, best_g, d);
+            if (os < best_score || (os == best_score && og < best_g)) {
+                best_score = os;
+                best_g = og;
+            }
+        }
+        if (n >= a.max_cells) {
+            if (lane == 0) atomicExch(a.error, 1u);
+            break;
+        }
+        if (lane == 0) out[n] = (uint16_t)best_g;
+        n++;
+        pos = __fadd_rn(pos, a.bank.advance_px[best_g]);  // main.rs:176-178 (advance precomputed in f32)
+        __syncwarp();   // the window is rewritten by the next cell
+    }
+    if (lane == 0) *n_cells_out = n;
+}
+
 __global__ void __launch_bounds__(256) sum_of_squares_kernel(const uint8_t *xs, const uint8_t *ys, size_t len,
                                                              long long *out)
 {
@@ -241,6 +395,11 @@ extern "C" void *focr_ctx_stream(focr_ctx *ctx);
 int focr_internal_device(const focr_ctx *ctx);
 void focr_internal_count_launch(focr_ctx *ctx, int n);
 int focr_internal_fail(int code, const std::string &msg);
+void *focr_internal_stage_begin(focr_ctx *ctx, int stage);
+void focr_internal_stage_end(void *timer);
+void focr_internal_streams(focr_ctx *ctx, cudaStream_t out[3]);   // compute, H2D, D2H
+bool focr_internal_host_pinned(const void *p);
+void focr_internal_parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows);
 
 struct focr_glyph_bank {
     focr_ctx *ctx;
@@ -251,6 +410,8 @@ struct focr_glyph_bank {
     float origin_x;
     uint4 *tasks;          // row tasks per phase (GlyphBankDev), nullptr when a bitmap is too large for the packing
     uint32_t *task_off;
+    uint8_t *tiles;        // dense per-(phase, glyph) tiles (GlyphBankDev), nullptr when a bitmap does not fit a 32 x 32 tile
+    int tile_rows, tile_wb, tile_left;
 };
 
 #define FCU(call)                                                                                          \
@@ -269,7 +430,7 @@ extern "C" int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size
     for (size_t i = 0; i < (size_t)n_glyphs * 64; i++)
         if (rasters[i].offset + (size_t)rasters[i].w * rasters[i].h > n_pixel_bytes)
             return focr_internal_fail(FOCR_ERR_ARG, "focr_glyph_bank_create: raster outside the pixel buffer");
-    // the kernel accumulates Sum g*(g - 2*ref) in 32-bit integers (the reference's sum_of_squares is i64, main.rs:510-516):
+    // the kernels accumulate Sum g*(g - 2*ref) in 32-bit integers (the reference's sum_of_squares is i64, main.rs:510-516):
     // |term| <= 255*255 per pixel, so a bitmap must stay below 2^31 / 65025 = 33025 pixels (a ~180 px glyph)
     for (size_t i = 0; i < (size_t)n_glyphs * 64; i++)
         if ((uint64_t)rasters[i].w * rasters[i].h * 65025ull >= (1ull << 31))
@@ -323,6 +484,37 @@ extern "C" int focr_glyph_bank_create(focr_ctx *ctx, const uint8_t *pixels, size
             FCU(cudaMemcpy(b->task_off, toff.data(), 65 * 4, cudaMemcpyHostToDevice));
         }
     }
+    // dense tiles (focr_decode_tile_kernel): all bitmaps of the bank on one canvas grid of tile_rows x tile_wb bytes whose
+    // first column is canvas column dint + tile_left; rows above the canvas are dropped (always clipped)
+    b->tiles = nullptr;
+    {
+        int left = 0x7fffffff, right = -0x7fffffff, bottom = 0;
+        for (auto &r : rs)
+            if (r.w && r.h) {
+                left = std::min(left, (int)r.left);
+                right = std::max(right, (int)r.left + (int)r.w);
+                bottom = std::max(bottom, (int)r.top + (int)r.h);
+            }
+        if (left <= right && bottom >= 1 && bottom <= 32 && right - left <= 32) {
+            b->tile_left = left;
+            b->tile_rows = bottom;
+            b->tile_wb = (right - left + 15) & ~15;
+            const size_t tile = (size_t)b->tile_rows * b->tile_wb;
+            std::vector<uint8_t> tiles((size_t)64 * n_glyphs * tile, 0);
+            for (uint32_t ph = 0; ph < 64; ph++)
+                for (uint32_t g = 0; g < n_glyphs; g++) {
+                    const focr_glyph_raster &r = rasters[(size_t)g * 64 + ph];
+                    uint8_t *t = tiles.data() + ((size_t)ph * n_glyphs + g) * tile;
+                    for (int y = 0; y < (int)r.h; y++) {
+                        const int cy = (int)r.top + y;
+                        if (cy < 0) continue;
+                        memcpy(t + (size_t)cy * b->tile_wb + ((int)r.left - left), pixels + r.offset + (size_t)y * r.w, r.w);
+                    }
+                }
+            FCU(cudaMalloc((void **)&b->tiles, tiles.size()));
+            FCU(cudaMemcpy(b->tiles, tiles.data(), tiles.size(), cudaMemcpyHostToDevice));
+        }
+    }
     FCU(cudaMemcpy(b->pixels, padded.data(), padded.size(), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(b->rasters, rs.data(), rs.size() * sizeof(focr_glyph_raster), cudaMemcpyHostToDevice));
     FCU(cudaMemcpy(b->advance, advance_px, n_glyphs * sizeof(float), cudaMemcpyHostToDevice));
@@ -339,18 +531,20 @@ extern "C" void focr_glyph_bank_destroy(focr_glyph_bank *b)
     cudaFree(b->advance);
     cudaFree(b->tasks);
     cudaFree(b->task_off);
+    cudaFree(b->tiles);
     delete b;
 }
 
-// Grow-only scratch per device (device buffers + pinned staging for the results): a cudaMalloc / cudaFree pair per buffer
-// and call cost more than the decode kernel (12 ms of a 31 ms call for 32 pages), and cudaFree synchronises the device.
+// Grow-only scratch per device, two slots (device buffers + pinned staging): a cudaMalloc / cudaFree pair per buffer and
+// call costs more than the decode kernel, and cudaFree synchronises the device.
 namespace {
-struct DecodeScratch {
-    std::mutex mu;
-    void *dev[4] = {nullptr, nullptr, nullptr, nullptr};
+constexpr uint32_t FD_CHUNK = 16;   // pages per chunk: 16 x 232 lines / 4 = 928 blocks, one full wave of the decode kernel
+struct DecodeSlot {
+    void *dev[4] = {nullptr, nullptr, nullptr, nullptr};   // band, glyphs, cells, error flag
     size_t dev_cap[4] = {0, 0, 0, 0};
-    void *host[2] = {nullptr, nullptr};
-    size_t host_cap[2] = {0, 0};
+    void *host[3] = {nullptr, nullptr, nullptr};           // glyphs, cells + error flag, band staging (pageable callers)
+    size_t host_cap[3] = {0, 0, 0};
+    cudaEvent_t ev_h2d = nullptr, ev_k = nullptr, ev_d2h = nullptr;
     void *dev_buf(int i, size_t want)
     {
         if (want > dev_cap[i]) {
@@ -371,6 +565,17 @@ struct DecodeScratch {
         }
         return host[i];
     }
+    bool events()
+    {
+        if (ev_h2d) return true;
+        return cudaEventCreateWithFlags(&ev_h2d, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&ev_k, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&ev_d2h, cudaEventDisableTiming) == cudaSuccess;
+    }
+};
+struct DecodeScratch {
+    std::mutex mu;
+    DecodeSlot slot[2];
 };
 DecodeScratch g_decode_scratch[64];
 }  // namespace
@@ -386,93 +591,161 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
         return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: bad argument");
     if (page_stride < (size_t)r_w * r_h) return focr_internal_fail(FOCR_ERR_ARG, "page_stride smaller than a page");
     const size_t strip = (size_t)width * line_height;
+    if (strip == 0) return focr_internal_fail(FOCR_ERR_UNSUPPORTED, "empty line rectangle");
+    // which kernel: dense tiles when the bank has them and the padded strips fit, else row tasks, else whole glyphs per lane
+    const int ox = (int)bank->origin_x;
+    const bool tiles = bank->tiles && ox + bank->tile_left >= -FD_PAD && ox + bank->tile_left + bank->tile_wb + 4 <= FD_PAD &&
+                       !getenv("FOCR_DECODE_LEGACY");
     const bool row_tasks = bank->tasks && bank->n_glyphs <= FD_MAX_SCORES;
-    const size_t smem_bytes = ((strip * FD_WARPS + 16 + 15) & ~(size_t)15) + (row_tasks ? FD_WARPS * FD_MAX_SCORES * 4 : 0);
-    if (smem_bytes > 200 * 1024 + 16 || strip == 0)
+    size_t smem_bytes;
+    if (tiles) {
+        const size_t sp = (width + 2 * FD_PAD + 3) & ~(size_t)3;
+        smem_bytes = FD_WARPS * (((sp * line_height + 16 + 15) & ~(size_t)15) + (size_t)bank->tile_rows * bank->tile_wb);
+    } else {
+        smem_bytes = ((strip * FD_WARPS + 16 + 15) & ~(size_t)15) + (row_tasks ? FD_WARPS * FD_MAX_SCORES * 4 : 0);
+    }
+    if (smem_bytes > 200 * 1024 + 16)
         return focr_internal_fail(FOCR_ERR_UNSUPPORTED, "line rectangle too large for shared memory");
     FCU(cudaSetDevice(focr_internal_device(ctx)));
-    cudaStream_t st = (cudaStream_t)focr_ctx_stream(ctx);
+    cudaStream_t streams[3];
+    focr_internal_streams(ctx, streams);
+    cudaStream_t st = streams[0], st_h2d = streams[1], st_d2h = streams[2];
     // candidate rectangles per page: i = 0.. until the crop height is 0 (main.rs:199-207)
     const uint32_t cand = y_start >= r_h ? 0 : (r_h - y_start + line_advance - 1) / line_advance;
     if (cand > max_lines)
         return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: the page has " + std::to_string(cand) +
                                                     " candidate lines, max_lines is " + std::to_string(max_lines));
-    uint8_t *d_pages = nullptr;
-    uint16_t *d_glyphs = nullptr;
-    uint32_t *d_cells = nullptr;
-    unsigned int *d_err = nullptr;
-    const size_t n_lines_tot = (size_t)n_pages * max_lines;
-    // Only the band the rectangles can touch goes to the device: columns [x_start, x_start+width) and rows from y_start
-    // (crop_imm's clamping, main.rs:201-203, applied once here); the kernel sees it as a page of its own with x_start =
-    // y_start = 0.  For BASELINE config 4 that is 608 of 2480 columns: 4x less H2D traffic, which is what bounds this path.
+    // Only the band the rectangles can touch goes to the device: columns [x_start, x_start+width) of the rows from y_start on
+    // (crop_imm's clamping, main.rs:201-203, applied once here); the kernel sees it as pages of `bw` columns with x_start = 0.
+    // For BASELINE config 4 that is 608 of 2480 columns: 4x less H2D traffic, which is what bounds this path.
     const uint32_t bx = std::min(x_start, r_w), by = std::min(y_start, r_h);
-    const uint32_t bw = std::min(width, r_w - bx), bh = r_h - by;
-    const size_t band_bytes = (size_t)bw * bh;
+    const uint32_t bw = std::min(width, r_w - bx);
+    if (cand == 0 || bw == 0) {   // no rectangle has a pixel: every strip is empty / "all white" (main.rs:205-211)
+        for (uint32_t p = 0; p < n_pages; p++) n_lines_host[p] = 0;
+        return FOCR_OK;
+    }
+    const size_t band_page = (size_t)bw * r_h;            // device pages keep all r_h rows; rows above `by` are never read
+    const size_t lines_chunk = (size_t)FD_CHUNK * max_lines;
+    const bool staged = !focr_internal_host_pinned(pages_host);
     DecodeScratch &sc = g_decode_scratch[focr_internal_device(ctx) & 63];
     std::lock_guard<std::mutex> lock(sc.mu);   // calls on one device share the scratch
-    d_pages = (uint8_t *)sc.dev_buf(0, std::max<size_t>(band_bytes * n_pages, 1));
-    d_glyphs = (uint16_t *)sc.dev_buf(1, n_lines_tot * max_cells * 2);
-    d_cells = (uint32_t *)sc.dev_buf(2, n_lines_tot * 4);
-    d_err = (unsigned int *)sc.dev_buf(3, 4);
-    uint16_t *g = (uint16_t *)sc.host_buf(0, n_lines_tot * max_cells * 2);
-    uint32_t *c = (uint32_t *)sc.host_buf(1, n_lines_tot * 4 + 4);
-    if (!d_pages || !d_glyphs || !d_cells || !d_err || !g || !c)
-        return focr_internal_fail(FOCR_ERR_NOMEM, "focr_decode_pages: scratch allocation failed");
-    FCU(cudaMemsetAsync(d_cells, 0xFF, n_lines_tot * 4, st));
-    FCU(cudaMemsetAsync(d_err, 0, 4, st));
-    if (band_bytes)
-        for (uint32_t p = 0; p < n_pages; p++)
-            FCU(cudaMemcpy2DAsync(d_pages + p * band_bytes, bw, pages_host + p * page_stride + (size_t)by * r_w + bx, r_w, bw,
-                                  bh, cudaMemcpyHostToDevice, st));
-    DecodeArgs a;
-    a.pages = d_pages;
-    a.page_stride = band_bytes;
-    a.r_w = bw;
-    a.r_h = bh;
-    a.n_pages = n_pages;
-    a.x_start = 0;
-    a.y_start = 0;
-    a.width = width;
-    a.line_height = line_height;
-    a.line_advance = line_advance;
-    a.max_lines = max_lines;
-    a.max_cells = max_cells;
-    a.bank.pixels = bank->pixels;
-    a.bank.rasters = bank->rasters;
-    a.bank.advance_px = bank->advance;
-    a.bank.n_glyphs = bank->n_glyphs;
-    a.bank.tasks = row_tasks ? bank->tasks : nullptr;
-    a.bank.task_off = bank->task_off;
-    a.origin_x = bank->origin_x;
-    a.glyphs = d_glyphs;
-    a.n_cells = d_cells;
-    a.error = d_err;
-    FCU(cudaFuncSetAttribute(focr_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-    dim3 grid((max_lines + FD_WARPS - 1) / FD_WARPS, n_pages);
-    focr_decode_kernel<<<grid, FD_WARPS * 32, smem_bytes, st>>>(a);
-    FCU(cudaGetLastError());
-    focr_internal_count_launch(ctx, 1);
-    FCU(cudaMemcpyAsync(g, d_glyphs, n_lines_tot * max_cells * 2, cudaMemcpyDeviceToHost, st));
-    FCU(cudaMemcpyAsync(c, d_cells, n_lines_tot * 4, cudaMemcpyDeviceToHost, st));
-    FCU(cudaMemcpyAsync(c + n_lines_tot, d_err, 4, cudaMemcpyDeviceToHost, st));
-    FCU(cudaStreamSynchronize(st));
-    const unsigned int err = c[n_lines_tot];
-    if (err) return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: a line needs more than max_cells cells");
-    // compact like decode_image: skip all-white strips, stop at the first empty text (main.rs:205-216)
-    for (uint32_t p = 0; p < n_pages; p++) {
-        uint32_t n = 0;
-        for (uint32_t i = 0; i < cand; i++) {
-            const uint32_t cells = c[(size_t)p * max_lines + i];
-            if (cells == 0xFFFFFFFFu) continue;  // skipped strip
-            if (cells == 0) break;               // empty text ends the page
-            const size_t dst = ((size_t)p * max_lines + n) * max_cells, srcp = ((size_t)p * max_lines + i) * max_cells;
-            for (uint32_t k = 0; k < cells; k++) glyphs_host[dst + k] = g[srcp + k];
-            n_cells_host[(size_t)p * max_lines + n] = cells;
-            line_y_host[(size_t)p * max_lines + n] = y_start + i * line_advance;
-            n++;
-        }
-        n_lines_host[p] = n;
+    const uint32_t CH = std::min(FD_CHUNK, n_pages);
+    for (auto &sl : sc.slot) {
+        if (!sl.dev_buf(0, band_page * CH) || !sl.dev_buf(1, (size_t)CH * max_lines * max_cells * 2) ||
+            !sl.dev_buf(2, (size_t)CH * max_lines * 4) || !sl.dev_buf(3, 4) ||
+            !sl.host_buf(0, (size_t)CH * max_lines * max_cells * 2) || !sl.host_buf(1, (size_t)CH * max_lines * 4 + 4) ||
+            (staged && !sl.host_buf(2, band_page * CH)) || !sl.events())
+            return focr_internal_fail(FOCR_ERR_NOMEM, "focr_decode_pages: scratch allocation failed");
+        if (n_pages <= FD_CHUNK) break;   // a single chunk only needs one slot
     }
+    (void)lines_chunk;
+    bool cells_error = false;
+    // a finished chunk: compact like decode_image -- skip all-white strips, stop at the first empty text (main.rs:205-216)
+    auto finish = [&](uint32_t p0, uint32_t nB, DecodeSlot &sl) {
+        const uint16_t *g = (const uint16_t *)sl.host[0];
+        const uint32_t *c = (const uint32_t *)sl.host[1];
+        if (c[(size_t)nB * max_lines]) cells_error = true;
+        for (uint32_t q = 0; q < nB; q++) {
+            const uint32_t p = p0 + q;
+            uint32_t n = 0;
+            for (uint32_t i = 0; i < cand; i++) {
+                const uint32_t cells = c[(size_t)q * max_lines + i];
+                if (cells == 0xFFFFFFFFu) continue;  // skipped strip
+                if (cells == 0) break;               // empty text ends the page
+                const size_t dst = ((size_t)p * max_lines + n) * max_cells, srcp = ((size_t)q * max_lines + i) * max_cells;
+                memcpy(glyphs_host + dst, g + srcp, (size_t)std::min(cells, max_cells) * 2);
+                n_cells_host[(size_t)p * max_lines + n] = cells;
+                line_y_host[(size_t)p * max_lines + n] = y_start + i * line_advance;
+                n++;
+            }
+            n_lines_host[p] = n;
+        }
+    };
+    const uint32_t n_chunks = (n_pages + CH - 1) / CH;
+    for (uint32_t ci = 0; ci < n_chunks; ci++) {
+        const uint32_t p0 = ci * CH, nB = std::min(CH, n_pages - p0);
+        DecodeSlot &sl = sc.slot[ci & 1];
+        if (ci >= 2) {   // the slot's previous chunk: wait for its results, hand them to the caller
+            FCU(cudaEventSynchronize(sl.ev_d2h));
+            finish((ci - 2) * CH, CH, sl);
+        }
+        uint8_t *d_band = (uint8_t *)sl.dev[0];
+        const uint8_t *src0 = pages_host + (size_t)p0 * page_stride;
+        if (staged) {   // pageable caller: host threads gather the band into pinned staging, then one contiguous copy
+            uint8_t *stg = (uint8_t *)sl.host[2];
+            for (uint32_t q = 0; q < nB; q++)
+                focr_internal_parallel_copy(stg + q * band_page + (size_t)by * bw, bw, src0 + q * page_stride + (size_t)by * r_w + bx, r_w,
+                                            bw, r_h - by);
+            FCU(cudaMemcpyAsync(d_band + (size_t)by * bw, stg + (size_t)by * bw, band_page * nB - (size_t)by * bw, cudaMemcpyHostToDevice,
+                                st_h2d));
+        } else if (page_stride == (size_t)r_w * r_h) {   // contiguous pinned pages: ONE strided copy for the whole chunk
+            FCU(cudaMemcpy2DAsync(d_band + (size_t)by * bw, bw, src0 + (size_t)by * r_w + bx, r_w, bw, (size_t)nB * r_h - by,
+                                  cudaMemcpyHostToDevice, st_h2d));
+        } else {
+            for (uint32_t q = 0; q < nB; q++)
+                FCU(cudaMemcpy2DAsync(d_band + q * band_page + (size_t)by * bw, bw, src0 + q * page_stride + (size_t)by * r_w + bx, r_w,
+                                      bw, r_h - by, cudaMemcpyHostToDevice, st_h2d));
+        }
+        FCU(cudaEventRecord(sl.ev_h2d, st_h2d));
+        FCU(cudaStreamWaitEvent(st, sl.ev_h2d, 0));
+        FCU(cudaMemsetAsync(sl.dev[2], 0xFF, (size_t)nB * max_lines * 4, st));
+        FCU(cudaMemsetAsync(sl.dev[3], 0, 4, st));
+        DecodeArgs a;
+        a.pages = d_band;
+        a.page_stride = band_page;
+        a.r_w = bw;
+        a.r_h = r_h;
+        a.n_pages = nB;
+        a.x_start = 0;
+        a.y_start = by;
+        a.width = width;
+        a.line_height = line_height;
+        a.line_advance = line_advance;
+        a.max_lines = max_lines;
+        a.max_cells = max_cells;
+        a.bank.pixels = bank->pixels;
+        a.bank.rasters = bank->rasters;
+        a.bank.advance_px = bank->advance;
+        a.bank.n_glyphs = bank->n_glyphs;
+        a.bank.tasks = row_tasks ? bank->tasks : nullptr;
+        a.bank.task_off = bank->task_off;
+        a.bank.tiles = bank->tiles;
+        a.bank.tile_rows = bank->tile_rows;
+        a.bank.tile_wb = bank->tile_wb;
+        a.bank.tile_left = bank->tile_left;
+        a.origin_x = bank->origin_x;
+        a.glyphs = (uint16_t *)sl.dev[1];
+        a.n_cells = (uint32_t *)sl.dev[2];
+        a.error = (unsigned int *)sl.dev[3];
+        dim3 grid((max_lines + FD_WARPS - 1) / FD_WARPS, nB);
+        void *tm = focr_internal_stage_begin(ctx, FOCR_STAGE_DECODE);
+        if (tiles && bank->tile_wb == 16) {
+            FCU(cudaFuncSetAttribute(focr_decode_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+            focr_decode_tile_kernel<1><<<grid, FD_WARPS * 32, smem_bytes, st>>>(a);
+        } else if (tiles) {
+            FCU(cudaFuncSetAttribute(focr_decode_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+            focr_decode_tile_kernel<2><<<grid, FD_WARPS * 32, smem_bytes, st>>>(a);
+        } else {
+            FCU(cudaFuncSetAttribute(focr_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+            focr_decode_kernel<<<grid, FD_WARPS * 32, smem_bytes, st>>>(a);
+        }
+        focr_internal_stage_end(tm);
+        FCU(cudaGetLastError());
+        focr_internal_count_launch(ctx, 1);
+        FCU(cudaEventRecord(sl.ev_k, st));
+        FCU(cudaStreamWaitEvent(st_d2h, sl.ev_k, 0));
+        uint32_t *c = (uint32_t *)sl.host[1];
+        FCU(cudaMemcpyAsync(sl.host[0], sl.dev[1], (size_t)nB * max_lines * max_cells * 2, cudaMemcpyDeviceToHost, st_d2h));
+        FCU(cudaMemcpyAsync(c, sl.dev[2], (size_t)nB * max_lines * 4, cudaMemcpyDeviceToHost, st_d2h));
+        FCU(cudaMemcpyAsync(c + (size_t)nB * max_lines, sl.dev[3], 4, cudaMemcpyDeviceToHost, st_d2h));
+        FCU(cudaEventRecord(sl.ev_d2h, st_d2h));
+    }
+    for (uint32_t ci = (n_chunks >= 2 ? n_chunks - 2 : 0); ci < n_chunks; ci++) {
+        DecodeSlot &sl = sc.slot[ci & 1];
+        FCU(cudaEventSynchronize(sl.ev_d2h));
+        finish(ci * CH, std::min(CH, n_pages - ci * CH), sl);
+    }
+    if (cells_error) return focr_internal_fail(FOCR_ERR_ARG, "focr_decode_pages: a line needs more than max_cells cells");
     return FOCR_OK;
 }
 

@@ -45,10 +45,10 @@ class Context:
 
     def profile_read(self):
         """{stage: (total ms, launches)} since the last read; synchronises."""
-        ms = np.zeros(5, np.float64)
-        n = np.zeros(5, np.uint64)
+        ms = np.zeros(6, np.float64)
+        n = np.zeros(6, np.uint64)
         check(lib().focr_ctx_profile_read(self._h, ptr(ms), ptr(n)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("invert", "stats", "scan", "finalize", "exact"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("invert", "stats", "scan", "finalize", "exact", "decode"))}
 
     def close(self):
         if self._h:

@@ -102,8 +102,9 @@ uint64_t focr_ctx_launch_count(const focr_ctx *ctx);
  * recorded since the last read into ms_out[FOCR_STAGE_*] / launches_out[FOCR_STAGE_*] and resets.
  * This is how bench.py measures the correlation kernel's average launch duration live. */
 /* FOCR_STAGE_EXACT (the exact f64 pass over the tensor-core screen's survivors) is a sub-interval of FOCR_STAGE_SCAN. */
+/* FOCR_STAGE_DECODE is the focr line-decode kernel (focr_decode_pages). */
 enum { FOCR_STAGE_INVERT = 0, FOCR_STAGE_STATS = 1, FOCR_STAGE_SCAN = 2, FOCR_STAGE_FINALIZE = 3, FOCR_STAGE_EXACT = 4,
-       FOCR_N_STAGES = 5 };
+       FOCR_STAGE_DECODE = 5, FOCR_N_STAGES = 6 };
 int focr_ctx_profile(focr_ctx *ctx, int enable);
 int focr_ctx_profile_read(focr_ctx *ctx, double *ms_out, uint64_t *launches_out);
 

@@ -1,0 +1,14 @@
+set -x
+CMD="python bench.py --steps 1 --warmup 3 --pages 32 --no-cpu --no-small --no-focr --no-config5"
+timeout 280 $CMD > gpurun_out/r2_plain_bench.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu_launch.log 2>&1
+echo "launch list rc=$?"
+timeout 280 python tools/prof_run.py > gpurun_out/r2_plain_prof.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_tc_kernel -s 1 -c 1 -f -o gpurun_out/r2_prof_scan_tc python tools/prof_run.py > gpurun_out/r2_ncu_a.log 2>&1
+echo "scan_tc rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:cand_exact|window_stats|stage_invert|row_cut|select_kernel|sort_emit" -s 6 -c 6 -f -o gpurun_out/r2_prof_tail python tools/prof_run.py > gpurun_out/r2_ncu_b.log 2>&1
+echo "tail rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:focr_decode -s 1 -c 1 -f -o gpurun_out/r2_prof_focr python tools/prof_run.py > gpurun_out/r2_ncu_c.log 2>&1
+echo "focr rc=$?"
+cat gpurun_out/r2_plain_prof.log | tail -3
+ls -la gpurun_out/
