@@ -45,13 +45,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Build the product library.  With FOCR_TC_EXPERIMENTS=1 in the environment the kernel's experiment hooks are compiled
     in and the result goes to libfocr_b200_exp.so (tools/ select it with FOCR_B200_LIB); the product library is untouched."""
     exp = bool(os.environ.get("FOCR_TC_EXPERIMENTS"))
+    variant = os.environ.get("FOCR_BUILD_VARIANT", "")   # tools/: "name:-DFLAG ..." builds libfocr_b200_<name>.so with extra flags
     out = OUT.replace(".so", "_exp.so") if exp else OUT
+    if variant:
+        out = OUT.replace(".so", "_" + variant.split(":")[0] + ".so")
     stamp = out + ".stamp"
-    dg = _digest() + ("+exp" if exp else "")
+    dg = _digest() + ("+exp" if exp else "") + variant
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dg:
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DFOCR_TC_EXPERIMENTS"] if exp else []  # tools/tc_trace.py, tools/tc_modes.py, tools/tc_timeline.py
+    if variant and ":" in variant:
+        extra += variant.split(":", 1)[1].split()
     cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -33,15 +33,34 @@ def rust_f32(v) -> str:
     return np.format_float_positional(v, unique=True, trim="-")
 
 
+def _narrow16(v: np.ndarray) -> np.ndarray:
+    """The image crate's u16 -> u8 sample conversion (`FromPrimitive<u16> for u8`): (c + 128) / 257, not c >> 8."""
+    return ((v.astype(np.uint32) + 128) // 257).astype(np.uint8)
+
+
 def load_luma8(path: str) -> np.ndarray:
     """image::open(path).into_luma8() (ncc.rs:575, main.rs:429): u8 [h, w].  Colour images are reduced with the image
-    crate's integer Rec.709 weights, (2126 r + 7152 g + 722 b) / 10000, alpha dropped."""
+    crate's integer Rec.709 weights, (2126 r + 7152 g + 722 b) / 10000, alpha dropped; 16-bit samples are reduced in
+    16 bits first and then narrowed with (c + 128) / 257 like the crate does."""
     from PIL import Image
 
+    try:   # Pillow narrows 16-bit colour on load; OpenCV keeps the samples
+        import cv2
+
+        raw = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        if raw is not None and raw.dtype == np.uint16:
+            if raw.ndim == 2:
+                return _narrow16(raw)
+            if raw.shape[2] == 2:                      # gray + alpha
+                return _narrow16(raw[..., 0])
+            b, g, r = (raw[..., i].astype(np.uint64) for i in range(3))   # BGR[A]
+            return _narrow16((2126 * r + 7152 * g + 722 * b) // 10000)
+    except ImportError:
+        pass
     im = Image.open(path)
     if im.mode in ("L", "1", "P", "I;16", "I", "F", "LA", "PA"):
         if im.mode in ("I;16", "I"):
-            return (np.asarray(im, np.uint32) >> 8).astype(np.uint8)
+            return _narrow16(np.asarray(im, np.uint32))
         if im.mode in ("P", "PA"):
             im = im.convert("RGB")
         else:

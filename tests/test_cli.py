@@ -29,6 +29,13 @@ def test_load_luma8_gray_and_rec709(pkg, tmp_path):
     r32 = rgb.astype(np.uint32)
     exp = ((2126 * r32[..., 0] + 7152 * r32[..., 1] + 722 * r32[..., 2]) // 10000).astype(np.uint8)
     assert np.array_equal(load_luma8(str(tmp_path / "c.png")), exp)
+    # 16-bit gray: the image crate narrows with (c + 128) / 257 (129 -> 1, 127 -> 0), not with >> 8
+    g16 = rng.integers(0, 65536, (9, 13), dtype=np.uint16)
+    g16[0, :4] = (127, 128, 129, 65535)
+    Image.fromarray(g16).save(tmp_path / "g16.png")
+    got = load_luma8(str(tmp_path / "g16.png"))
+    assert np.array_equal(got, ((g16.astype(np.uint32) + 128) // 257).astype(np.uint8))
+    assert got[0, :4].tolist() == [0, 0, 1, 255]
 
 
 def test_flags_mirror_the_reference(pkg):

@@ -9,6 +9,7 @@ import bench
 from font_ocr_b200 import focr, native, ncc
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+THR = float(sys.argv[2]) if len(sys.argv) > 2 else 0.8
 pkg, font, bank_h = bench.make_bank()
 tpls = [t.pixels for t in bank_h.templates]
 T = len(tpls)
@@ -20,7 +21,7 @@ cnt = torch.empty(P * T, dtype=torch.int32, device="cuda")
 for i in range(2):
     if i == 1:
         ctx.profile(True); ctx.profile_read()
-    ncc.scan_pages_device(ctx, bank, pages.data_ptr(), bench.R_W * bench.R_H, bench.R_W, bench.R_W, bench.R_H, P, 0.8, 1024,
+    ncc.scan_pages_device(ctx, bank, pages.data_ptr(), bench.R_W * bench.R_H, bench.R_W, bench.R_W, bench.R_H, P, THR, 1024,
                           out.data_ptr(), cnt.data_ptr())
 pr = ctx.profile_read(); ctx.profile(False)
 print("scan", {k: round(v[0] / P, 4) for k, v in pr.items()}, "ms/page", flush=True)

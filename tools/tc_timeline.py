@@ -19,7 +19,7 @@ pages = torch.from_numpy(bench.make_pages(pkg, bank_h, P, 0)).cuda()
 out = torch.empty(P * T * 1024 * 8, dtype=torch.uint8, device="cuda")
 cnt = torch.empty(P * T, dtype=torch.int32, device="cuda")
 for i in range(2):
-    ncc.scan_pages_device(ctx, bank, pages.data_ptr(), bench.R_W * bench.R_H, bench.R_W, bench.R_W, bench.R_H, P, 0.8, 1024,
+    ncc.scan_pages_device(ctx, bank, pages.data_ptr(), bench.R_W * bench.R_H, bench.R_W, bench.R_W, bench.R_H, P, float(os.environ.get("THR", "0.8")), 1024,
                           out.data_ptr(), cnt.data_ptr())
 ctx.sync()
 names = {0: ("issuer 0", ["wait t_empty", "go", "issued", "committed"]),
