@@ -99,6 +99,11 @@ def _ncc_parser():
     ap.add_argument("--raw", action="store_true")
     ap.add_argument("--device", type=int, default=0, help="(extension) CUDA device")
     ap.add_argument("--batch", type=int, default=16, help="(extension) pages per GPU batch")
+    ap.add_argument("--spaces", action="store_true",
+                    help="(extension, off by default) insert spaces where the gap between two kept hits exceeds the left glyph's "
+                         "advance; the reference does not detect spaces (README.md:46)")
+    ap.add_argument("--space-advance", type=float, default=None,
+                    help="(extension) advance of a space in pixels for --spaces (default: the font's U+0020 advance at -t)")
     ap.add_argument("--max-matches", type=int, default=1024,
                     help="(extension) hits kept per template and page; the reference's MAX_MATCHES is 1024 (ncc.rs:31)")
     return ap
@@ -185,6 +190,12 @@ def ncc_main(argv=None, out=None) -> int:
         out.write("".join(l + "\n" for l in raw_lines))
         return 0
     f32 = np.float32
+    adv_px, space_px = {}, 0.0
+    if args.spaces:   # pen advances in pixels, f32 like main.rs:176-178
+        upem = f32(font.units_per_em)
+        px = lambda ch: float(f32(f32(font.advance(font.glyph_for_char(ch))[0] / upem) * f32(args.text_size)))
+        adv_px = {ch: px(ch) for ch in args.alphabet}
+        space_px = args.space_advance if args.space_advance is not None else px(" ")
     for i in range(len(images)):                    # pages.sort_by_key(|(i, _)| *i), ncc.rs:847
         for tpl, sel in page_lines.get(i, []):
             if args.csv:                            # ncc.rs:849-867
@@ -193,6 +204,9 @@ def ncc_main(argv=None, out=None) -> int:
                     x, y = int(m["x"]), int(m["y"])
                     out.write(f"{i},{ord(letters[int(t)])},{rust_f32(f32(x) + f32(w) * f32(0.5))},"
                               f"{rust_f32(f32(y) + f32(h) * f32(0.5))},{x},{y},{w},{h}\n")
+            elif args.spaces:                       # extension: the same line with detected spaces
+                line = [(letters[int(t)], int(m["x"]), int(m["y"]), m["similarity"]) for t, m in zip(tpl, sel)]
+                out.write(ncc.lines_to_text_with_spaces([line], adv_px, space_px)[0] + "\n")
             else:                                   # ncc.rs:869-876
                 out.write("".join(letters[int(t)] for t in tpl) + "\n")
     return 0

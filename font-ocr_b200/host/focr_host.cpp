@@ -2,6 +2,7 @@
 #include "focr_host.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <unordered_set>
 
@@ -53,6 +54,22 @@ std::vector<std::vector<MatchWithLetter>> process_hits(float anchor_threshold, i
         lines.push_back(std::move(dedup));
     }
     return lines;
+}
+
+std::u32string line_text_with_spaces(const std::vector<MatchWithLetter> &line, const std::function<float(uint32_t)> &advance_px,
+                                     float space_px)
+{
+    std::u32string out;
+    for (size_t i = 0; i < line.size(); i++) {
+        if (i > 0 && space_px > 0.f) {
+            // pen travel between the two hits minus what the left glyph itself advances = room taken by spaces
+            const float excess = (float)(line[i].rect.x - line[i - 1].rect.x) - advance_px(line[i - 1].letter);
+            const int k = excess > 0.f ? (int)std::floor(excess / space_px + 0.5f) : 0;
+            out.append((size_t)k, U' ');
+        }
+        out.push_back((char32_t)line[i].letter);
+    }
+    return out;
 }
 
 Searcher::Searcher(const uint8_t *gray, uint32_t width, uint32_t height)
@@ -139,6 +156,26 @@ std::vector<std::vector<DecodedLine>> decode_image_vec(focr_ctx *ctx, const focr
 // ------------------------------------------------------------------------------------------------
 // C hooks (include/focr_b200.h section 4): let the ctypes tests drive the C++ host mirror.
 using namespace focr_host;
+
+extern "C" int focr_host_line_text_with_spaces(const int32_t *xs, const uint32_t *letters, uint32_t n, const uint32_t *adv_letters,
+                                               const float *adv_px, uint32_t n_adv, float space_px, uint32_t *out, uint32_t out_cap,
+                                               uint32_t *n_out)
+{
+    if ((n && (!xs || !letters)) || (n_adv && (!adv_letters || !adv_px)) || !out || !n_out)
+        return focr_internal_fail(FOCR_ERR_ARG, "focr_host_line_text_with_spaces: NULL argument");
+    std::vector<MatchWithLetter> line(n);
+    for (uint32_t i = 0; i < n; i++) line[i] = MatchWithLetter{RectI{xs[i], 0, 0, 0}, 0.f, letters[i], i};
+    auto adv = [&](uint32_t letter) -> float {
+        for (uint32_t k = 0; k < n_adv; k++)
+            if (adv_letters[k] == letter) return adv_px[k];
+        return 0.f;
+    };
+    const std::u32string t = line_text_with_spaces(line, adv, space_px);
+    *n_out = (uint32_t)t.size();
+    if (t.size() > out_cap) return focr_internal_fail(FOCR_ERR_NOMEM, "focr_host_line_text_with_spaces: out_cap too small (see n_out)");
+    for (size_t i = 0; i < t.size(); i++) out[i] = (uint32_t)t[i];
+    return FOCR_OK;
+}
 
 extern "C" int focr_host_process_hits(const int32_t *xs, const int32_t *ys, const float *sims, const uint32_t *letters,
                                       uint32_t n, float anchor_threshold, int32_t overlap, uint32_t *out_index,

@@ -61,6 +61,15 @@ std::vector<std::pair<size_t, size_t>> partition_by(const T *xs, size_t n, Pred 
 std::vector<std::vector<MatchWithLetter>> process_hits(float anchor_threshold, int32_t overlap,
                                                        const std::vector<MatchWithLetter> &all_hits);
 
+// EXTENSION (opt-in; the reference "does not currently detect spaces", README.md:46): gaps between the kept hits of a line
+// that are wider than the left glyph's advance are filled with round(excess / space_px) spaces.  `line` is one output
+// line of process_hits (x ascending); advance_px(letter) is the glyph's pen advance in pixels (what a renderer moved the
+// pen by: ncc's template origin is the same for every letter, so hit x differences ARE pen advances), space_px the
+// advance of U+0020.  Hits keep their order; the result is the line's text as code points.  With space_px <= 0 nothing
+// is inserted (the reference's output).
+std::u32string line_text_with_spaces(const std::vector<MatchWithLetter> &line, const std::function<float(uint32_t)> &advance_px,
+                                     float space_px);
+
 // ncc.rs:128-141, 230-404: one page's search state.  search_c_u8 marshals exactly like the reference
 // and calls the library's ncc_8_u8 / ncc_16_u8 (the compat shim); the window statistics the reference
 // keeps in Searcher (SATs, patch_sum, patch_rnorm, start_end) live on the device instead.

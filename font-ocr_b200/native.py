@@ -29,7 +29,7 @@ SYMBOLS = [
     "focr_multi_glyph_bank_create", "focr_multi_glyph_bank_destroy", "focr_multi_decode_pages",
     "focr_ncc_scan", "focr_ncc_scan_device", "focr_process_hits_device", "focr_window_stats", "focr_ncc_numerators",
     "focr_glyph_bank_create", "focr_glyph_bank_destroy", "focr_decode_pages", "focr_sum_of_squares",
-    "focr_host_process_hits", "focr_host_search_c_u8",
+    "focr_host_process_hits", "focr_host_search_c_u8", "focr_host_line_text_with_spaces",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     l.focr_sum_of_squares.argtypes = [vp, vp, vp, sz, u32, vp]
     l.focr_process_hits_device.argtypes = [vp, vp, vp, u32, u32, u32, C.c_float, C.c_int32, u32, u32, vp, vp, vp, vp, vp, vp]
     l.focr_host_process_hits.argtypes = [vp, vp, vp, vp, u32, C.c_float, C.c_int32, vp, vp, vp]
+    l.focr_host_line_text_with_spaces.argtypes = [vp, vp, u32, vp, vp, u32, C.c_float, vp, u32, vp]
     l.focr_host_search_c_u8.argtypes = [vp, u32, u32, vp, u32, u32, C.c_float, vp, vp]
     _lib = l
     return l

@@ -335,6 +335,30 @@ def lines_to_text(lines):
     return ["".join(h[0] for h in line) for line in lines]
 
 
+def lines_to_text_with_spaces(lines, advance_px: dict, space_px: float):
+    """EXTENSION (opt-in; README.md:46 "does not currently detect spaces"): like lines_to_text, with spaces inserted where
+    the pen travel between two kept hits exceeds the left glyph's advance, through the C++ host mirror
+    (focr_host::line_text_with_spaces).  advance_px: {letter: advance in pixels}; space_px: advance of ' '."""
+    letters = np.array([ord(c) for c in advance_px], np.uint32)
+    adv = np.array([advance_px[c] for c in advance_px], np.float32)
+    out = []
+    for line in lines:
+        xs = np.array([h[1] for h in line], np.int32)
+        ls = np.array([ord(h[0]) for h in line], np.uint32)
+        cap = 8 * len(line) + 64
+        while True:
+            buf, n_out = np.zeros(cap, np.uint32), np.zeros(1, np.uint32)
+            rc = lib().focr_host_line_text_with_spaces(ptr(xs), ptr(ls), len(line), ptr(letters), ptr(adv), len(letters),
+                                                       C.c_float(space_px), ptr(buf), cap, ptr(n_out))
+            if rc == native.FOCR_ERR_NOMEM and int(n_out[0]) > cap:
+                cap = int(n_out[0])
+                continue
+            check(rc)
+            break
+        out.append("".join(chr(c) for c in buf[:int(n_out[0])]))
+    return out
+
+
 def host_process_hits(all_hits, anchor_threshold: float = 0.95, overlap: int = 5):
     """process_hits through the C++ host mirror (host/focr_host.cpp); same input/output as process_hits.
     Raises IndexError where the reference panics (no anchor line, ncc.rs:1040)."""

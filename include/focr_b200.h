@@ -260,6 +260,13 @@ int focr_sum_of_squares(focr_ctx *ctx, const uint8_t *xs_host, const uint8_t *ys
 int focr_host_process_hits(const int32_t *xs, const int32_t *ys, const float *sims, const uint32_t *letters,
                            uint32_t n, float anchor_threshold, int32_t overlap, uint32_t *out_index,
                            uint32_t *line_offsets, uint32_t *n_lines);
+/* EXTENSION, opt-in (the reference "does not currently detect spaces", README.md:46): the text of one output line of
+ * process_hits (hits in x order) with round(excess / space_px) spaces inserted wherever the pen travel between two hits
+ * exceeds the left glyph's advance.  adv_letters / adv_px give the advance in pixels per letter; out receives code points
+ * (n_out is always set; FOCR_ERR_NOMEM if out_cap is too small).  space_px <= 0 inserts nothing. */
+int focr_host_line_text_with_spaces(const int32_t *xs, const uint32_t *letters, uint32_t n, const uint32_t *adv_letters,
+                                    const float *adv_px, uint32_t n_adv, float space_px, uint32_t *out, uint32_t out_cap,
+                                    uint32_t *n_out);
 /* Searcher::new + Searcher::search_c_u8 (ncc.rs:231-261, 332-404) for one gray page and one tight
  * n_w x n_h needle; out needs 1024 entries.  Widths above 16 return FOCR_ERR_UNSUPPORTED
  * ("panic: not handled", ncc.rs:392). */

@@ -266,6 +266,23 @@ def lines_to_text(lines):
     return ["".join(h[0] for h in line) for line in lines]                       # ncc.rs:869-876
 
 
+def lines_to_text_with_spaces(lines, advance_px: dict, space_px: float):
+    """Restatement of the opt-in space-detection EXTENSION (not in the reference, README.md:46): between consecutive kept
+    hits of a line, round((x_i - x_{i-1} - advance(letter_{i-1})) / space_px) spaces when that excess is positive."""
+    f32 = np.float32
+    out = []
+    for line in lines:
+        s = []
+        for i, h in enumerate(line):
+            if i and space_px > 0:
+                excess = f32(f32(h[1] - line[i - 1][1]) - f32(advance_px.get(line[i - 1][0], 0.0)))
+                if excess > 0:
+                    s.append(" " * int(np.floor(f32(f32(excess / f32(space_px)) + f32(0.5)))))
+            s.append(h[0])
+        out.append("".join(s))
+    return out
+
+
 # --------------------------------------------------------------------------- focr (main.rs)
 def sum_of_squares(xs: np.ndarray, ys: np.ndarray) -> int:
     """main.rs:510-516 via the C restatement."""

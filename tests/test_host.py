@@ -63,3 +63,34 @@ def test_cpp_partition_by_anchoring(built_lib):
     f = np.float32
     hits = [("a", 0, 3, f(0.96)), ("b", 4, 3, f(0.96)), ("c", 8, 3, f(0.5))]
     assert ncc.lines_to_text(ncc.host_process_hits(hits, 0.95, 5)) == ["bc"]
+
+
+def test_space_detection_extension_matches_restatement(built_lib, oracle, font):
+    """Opt-in extension (README.md:46: the reference does not detect spaces): the C++ host mirror's
+    line_text_with_spaces against the oracle's restatement, on lines laid out with the reference's own pen arithmetic
+    (f32 advances, main.rs:176-178, hit x = floor of the pen position like a grid-snapping renderer), and the text with
+    its spaces must come back; without the flag's space advance nothing is inserted."""
+    from font_ocr_b200 import ncc
+
+    f32 = np.float32
+    upem = f32(font.units_per_em)
+    px = lambda ch: float(f32(f32(font.advance(font.glyph_for_char(ch))[0] / upem) * f32(13)))
+    alphabet = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/="
+    adv = {ch: px(ch) for ch in alphabet}
+    space = px(" ")
+    rng = np.random.default_rng(12)
+    lines, texts = [], []
+    for _ in range(20):
+        words = ["".join(rng.choice(list(alphabet), int(rng.integers(1, 9)))) for _ in range(int(rng.integers(1, 7)))]
+        text = (" " * int(rng.integers(1, 4))).join(words) if rng.random() < 0.5 else " ".join(words)
+        pen, line = f32(45.0), []
+        for ch in text:
+            if ch != " ":
+                line.append((ch, int(np.floor(pen)), 39, f32(0.97)))
+            pen = f32(pen + f32(adv.get(ch, space)))
+        lines.append(line)
+        texts.append(text)
+    got = ncc.lines_to_text_with_spaces(lines, adv, space)
+    assert got == oracle.lines_to_text_with_spaces(lines, adv, space)
+    assert got == texts
+    assert ncc.lines_to_text_with_spaces(lines, adv, 0.0) == [t.replace(" ", "") for t in texts] == ncc.lines_to_text(lines)
