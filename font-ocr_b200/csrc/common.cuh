@@ -20,7 +20,7 @@ namespace focr {
 // rowcount  : u32 [page][t][r_h]  hits per row, used to find the row where the n_out cap is reached
 // out       : focr_match [page][t][n_out] + counts [page][t]
 
-constexpr int PAGE_PAD_ROWS = 2;
+constexpr int PAGE_PAD_ROWS = 4;   // zero rows after a page: the scan's row pipeline reads up to 3 rows past the last one
 constexpr int MAX_TPL_W = 32;
 constexpr int MAX_TPL_H = 64;
 

@@ -71,7 +71,7 @@ constexpr int TC_EPI_UNITS = 4;       // 32-column units an epilogue warp holds 
 constexpr int TC_G = 4;               // rows per pipeline group: one mbarrier handshake per 4 rows
 constexpr int TC_RAW_GROUPS = 4;      // raw page-row ring (TMA destination): 4 groups x 4 rows x 160 B
 constexpr int TC_RAW_SLOTS = TC_RAW_GROUPS * TC_G;
-constexpr int TC_RAW_BYTES = 160;
+constexpr int TC_RAW_BYTES = 288;     // per raw slot: one page row of 128 + 16 (+16: boxes wider than 16) bytes, or two rows of 144 (packed mode)
 constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side may run ahead of the MMA (1 for tall boxes)
 constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: up to 4 groups x 4 output rows x 2 KB (2 for tall boxes)
@@ -96,7 +96,8 @@ struct TcParams {
     int pitch, r_w, r_h;
     int n_w, n_w2, n_h, np;   // n_w2: width of the second box size (ncls == 2)
     int ncls;          // box sizes in this launch group (1 or 2)
-    int n_hp;          // page rows an output row needs (n_h rounded up to 2 when np == 16)
+    int n_hp;          // ring slots (page rows) an output row spans: n_h rounded up to 2 (np == 16), n_h (np == 32), 4*ksteps - 1 (packed)
+    int packed;        // boxes at most 8 wide: ring slot r holds the 8-byte windows of page rows r AND r+1, a K chunk is two template rows
     int ksteps;        // tcgen05.mma kind::i8 per output row
     int nb;            // columns per launch = nsub * nbs
     int nsub;          // sub-blocks: jobs (accumulators) per output row
@@ -458,9 +459,11 @@ __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm,
                    nsub = p.nsub;
     const uint32_t b_lbo16 = (uint32_t)p.nbs, b_inc = 2 * b_lbo16;      // 16-byte units: K chunks of B are nbs columns apart
     const uint32_t b_sub = 2 * ksteps * b_lbo16, b2_sub = 2 * b_lbo16;   // sub-block strides of the B and B2 tiles
-    const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch : 256u) >> 4;
+    // the two 16-byte K chunks of an MMA: ring slots s, s+1 (np == 16), s, s+2 (packed: a slot already holds two page rows), or
+    // entries m, m+16 of one slot (np == 32)
+    const uint32_t a_lbo16 = (p.np == 16 ? (uint32_t)p.row_pitch * (p.packed ? 2u : 1u) : 256u) >> 4;
     const uint32_t pitch16 = (uint32_t)p.row_pitch >> 4;
-    const uint32_t a_step = p.np == 16 ? 2u : 1u;            // ring slots consumed per K step
+    const uint32_t a_step = p.np == 16 ? (p.packed ? 4u : 2u) : 1u;   // ring slots consumed per K step
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, version = 1
     const uint32_t a_lo0 = ((sm.ring & 0x3FFFFu) >> 4) | (a_lbo16 << 16);
     const uint32_t b_lo0 = ((sm.btile & 0x3FFFFu) >> 4) | (b_lbo16 << 16);
@@ -694,8 +697,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
             for (int r = 0; r < n_rows; r++, src += p.pitch) {
                 if (in_group == 0 && !first_round) TT(0, mbar_wait(raw_empty + rg, rgpar, p.wd, 1, slot, prog));
                 if (elect_one()) {
-                    mbar_expect_tx(raw_full + rg, row_bytes);
+                    mbar_expect_tx(raw_full + rg, p.packed ? 2 * row_bytes : row_bytes);
                     tma_bulk_g2s(raw + slot * TC_RAW_BYTES, src, row_bytes, raw_full + rg);
+                    // packed mode: the slot of page row r also needs row r+1 (PAGE_PAD_ROWS zero rows follow the page)
+                    if (p.packed) tma_bulk_g2s(raw + slot * TC_RAW_BYTES + 144, src + p.pitch, row_bytes, raw_full + rg);
                     if (in_group == TC_G - 1) mbar_arrive(raw_full + rg);
                 }
                 __syncwarp();
@@ -751,12 +756,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 for (int ee = lane; ee < p.n_entries; ee += 32) {
                     const uint32_t *wp = rw + (ee >> 2);
                     const int sh = (ee & 3) * 8;
-                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
                     uint4 o4;
-                    o4.x = __funnelshift_r(w0, w1, sh);
-                    o4.y = __funnelshift_r(w1, w2, sh);
-                    o4.z = __funnelshift_r(w2, w3, sh);
-                    o4.w = __funnelshift_r(w3, w4, sh);
+                    if (p.packed) {   // 8 bytes of this page row, 8 bytes of the next one (second half of the raw slot)
+                        const uint32_t *wq = wp + 36;
+                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], v0 = wq[0], v1 = wq[1], v2 = wq[2];
+                        o4.x = __funnelshift_r(w0, w1, sh);
+                        o4.y = __funnelshift_r(w1, w2, sh);
+                        o4.z = __funnelshift_r(v0, v1, sh);
+                        o4.w = __funnelshift_r(v1, v2, sh);
+                    } else {
+                        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                        o4.x = __funnelshift_r(w0, w1, sh);
+                        o4.y = __funnelshift_r(w1, w2, sh);
+                        o4.z = __funnelshift_r(w2, w3, sh);
+                        o4.w = __funnelshift_r(w3, w4, sh);
+                    }
                     *(uint4 *)(dst + ee * 16) = o4;
                     if (s < n_mirror) *(uint4 *)(dst + (size_t)p.ring * p.row_pitch + ee * 16) = o4;
                 }
@@ -1114,9 +1128,12 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     const uint32_t n_tpl = src[0].n_tpl + (ncls == 2 ? src[1].n_tpl : 0);
     tc.n_tpl = n_tpl;
     const uint32_t n_w_max = std::max(tc.n_w, tc.n_w2);
-    const uint32_t n_hp = np == 16 ? (n_h + 1) & ~1u : n_h;
-    tc.kchunks = n_h * (np / 16);
+    // boxes at most 8 wide: two template rows per 16-byte K chunk (ncc_8_u8's class, ncc.cpp:48-251)
+    tc.packed = np == 16 && n_w_max <= 8 && !getenv("FOCR_TC_NOPACK");
+    tc.kchunks = tc.packed ? (n_h + 1) / 2 : n_h * (np / 16);
     tc.ksteps = (tc.kchunks + 1) / 2;
+    const uint32_t n_hp = tc.packed ? 4 * tc.ksteps - 1 : (np == 16 ? (n_h + 1) & ~1u : n_h);
+    tc.n_hp = n_hp;
     // tall boxes: less look-ahead and a shorter A2 ring leave room for the B tile; boxes wider than 16 (np == 32) take
     // one ring slot per K step, so the issue loop can wrap and the mirror slots are not needed
     const bool tall = n_hp > 16;
@@ -1172,8 +1189,15 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
         const uint32_t blk = i / per_blk, r = i % per_blk, sub = r / per_sub, n = r % per_sub;
         const uint32_t col = sub * tc.nbsub + n;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
-            const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
             uint8_t *dst = &bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16];
+            if (tc.packed) {   // rows 2kc and 2kc+1, 8 bytes each (a row beyond n_h is zero)
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t row = 2 * kc + half;
+                    for (int q = 0; q < 8; q++) dst[8 * half + q] = row < n_h ? trows[(size_t)row * np + q] : 0;
+                }
+                continue;
+            }
+            const uint32_t row = np == 16 ? kc : kc / 2, boff = np == 16 ? 0 : (kc & 1) * 16;
             const uint8_t *sp = trows + (size_t)row * np + boff;
             for (int q = 0; q < 16; q++) dst[q] = (uint8_t)((sp[q] + (1u << tc.sshift) - 1u) >> tc.sshift);
         }
@@ -1239,7 +1263,8 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.ncls = tc.ncls;
     p.n_h = tc.n_h;
     p.np = tc.np;
-    p.n_hp = tc.np == 16 ? (tc.n_h + 1) & ~1u : tc.n_h;
+    p.n_hp = tc.n_hp;
+    p.packed = tc.packed ? 1 : 0;
     p.ksteps = tc.ksteps;
     p.nb = tc.nb;
     p.nsub = tc.nsub;

@@ -24,6 +24,8 @@ struct TcClass {
     uint32_t nsub = 0;      // sub-blocks per launch: every output row is nsub jobs (one accumulator each) sharing its operands
     uint32_t nbsub = 0;     // columns per sub-block = N of the MMAs (multiple of 32, <= 256)
     uint32_t n_blocks = 0;  // launches per chunk of pages
+    bool packed = false;    // boxes at most 8 wide: a K chunk holds TWO template rows of 8 bytes (half the MMA work of one row per chunk)
+    uint32_t n_hp = 0;      // ring slots (page rows) an output row spans
     uint32_t sshift = 0;    // boxes with more than 256 pixels: the screen runs on templates scaled by 2^-sshift (rounded up)
     uint32_t n_mirror = 0;  // ring slots stored twice (np == 16: an output row never wraps); 0 = the issue loop wraps
     uint32_t look_groups = 0, a2_groups = 0, ring_groups = 0;  // ring sizing of this group
