@@ -475,16 +475,17 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     const size_t PT = (size_t)nB * T;
     const size_t nR = std::max(nB, s.reserve_pages), PTR = nR * T;   // allocation sizes
     CU(s.inv.ensure(g.inv_page_stride * nR));
+    // statistics planes: the tcgen05 path reads ONE packed word per window and box size (sp / sp2) for boxes of at most 256
+    // pixels, sp + pf otherwise; only the SIMT kernel reads the sum-of-squares and f64 planes
+    bool any_unpacked = any_simt;
+    for (auto &gr : b->groups) any_unpacked |= use_tc(c, b, b->classes[gr.cls[0]]) && gr.tc.sshift != 0;
     CU(s.sp.ensure(g.plane_page_stride * nR * 4));
-    CU(s.pf.ensure(g.plane_page_stride * nR * 4));
-    if (any_simt) {   // only the SIMT kernel reads the sum-of-squares and f64 planes
+    if (any_unpacked) CU(s.pf.ensure(g.plane_page_stride * nR * 4));
+    if (any_simt) {
         CU(s.s2p.ensure(g.plane_page_stride * nR * 4));
         CU(s.rn.ensure(g.plane_page_stride * nR * 8));
     }
-    if (any_tc && any_pair) {
-        CU(s.sp2.ensure(g.plane_page_stride * nR * 4));
-        CU(s.pf2.ensure(g.plane_page_stride * nR * 4));
-    }
+    if (any_tc && any_pair) CU(s.sp2.ensure(g.plane_page_stride * nR * 4));   // paired groups are always packed (<= 256 pixels)
     CU(s.rowcount.ensure(PTR * g.r_h * 4));
     CU(s.hits.ensure((size_t)s.hits_per_page * nR * sizeof(Hit)));
     const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
@@ -535,11 +536,12 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         sa.rn = tc ? nullptr : s.rn.as<double>();
         sa.spitch = g.spitch;
         sa.plane_page_stride = g.plane_page_stride;
+        sa.pack = (tc && tcg->sshift == 0) ? 1 : 0;
         if (ch2) {
             sa.n_w2 = ch2->n_w;
             sa.inv_n_f2 = 1.0f / (float)(ch2->n_w * ch2->n_h);
             sa.sp2 = s.sp2.as<uint32_t>();
-            sa.pf2 = s.pf2.as<float>();
+            sa.pf2 = nullptr;
         }
         {
             StageTimer tm(c, FOCR_STAGE_STATS);
@@ -565,6 +567,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.rn = sa.rn;
         a.sp2 = sa.sp2;
         a.pf2 = sa.pf2;
+        a.pack = sa.pack;
         a.spitch = g.spitch;
         a.plane_page_stride = g.plane_page_stride;
         a.thr_d = (double)threshold;  // ncc.cpp:83

@@ -22,6 +22,9 @@ struct StatsArgs {
     float inv_n_f2;
     uint32_t *sp2;
     float *pf2;
+    // pack != 0 (boxes of at most 256 pixels, tcgen05 path): ONE word per window, `s_p | fix(norm_p) << 16` with norm_p in
+    // 11.5 fixed point (0xFFFF = constant window), written to sp / sp2; the pf planes are not touched.  Half the bytes.
+    int pack;
 };
 
 // what every scan kernel appends to
@@ -46,6 +49,7 @@ struct ScanArgs {
     const double *rn;
     const uint32_t *sp2 = nullptr;   // tcgen05 launch groups of two box sizes: the planes of the second one
     const float *pf2 = nullptr;
+    int pack = 0;                    // the sp planes hold packed words (StatsArgs::pack)
     int spitch;
     size_t plane_page_stride;
     double thr_d;

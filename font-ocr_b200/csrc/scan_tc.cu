@@ -88,7 +88,8 @@ constexpr size_t TC_SMEM_BUDGET = 220 * 1024;
 constexpr float TC_C0 = 16711680.f;               // 2^15 * 510 = 2^24 - 2^16: the constant term of the fp16 MMA
 constexpr float TC_KCAP = 8323072.f - 8192.f;     // C0 - 2^23 minus slack: largest b*S + a*P that keeps F in [2^23, 2^24)
 constexpr float TC_BIG = 60000.f;                 // fp16-representable "never" marker (BIG*BIG = 3.6e9 >> any acc)
-constexpr float TC_MARGIN = 256.f;                // absolute slack of the tensor-core normalisation, in units of acc (error budget < 60)
+constexpr float TC_MARGIN = 256.f;                // absolute slack of the tensor-core normalisation, in units of acc (error budget < 60,
+                                                  // + a * 2^-6 <= 64 for norm_p rounded to 1/32 in the packed statistics word)
 
 struct TcParams {
     const uint8_t *inv;
@@ -121,6 +122,7 @@ struct TcParams {
     uint32_t col_base;        // this launch's first column within the group (N-block * nb)
     const uint32_t *sp[2];    // window statistics planes per box size
     const float *pf[2];
+    int pack;                 // sp holds `s_p | fix11.5(norm_p) << 16` per window (0xFFFF: constant window), pf is unused
     int spitch;
     size_t plane_page_stride;
     Hit *cands;               // candidate lists, one PRIVATE list per epilogue warp: [grid*TC_LISTS_PER_CTA][cand_cap] {group column, y<<16|x, -, page}
@@ -816,20 +818,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
                 }
                 const int y = it.ys0 + (int)(o - item_o0);
                 const size_t rowoff = (size_t)it.page * p.plane_page_stride + (size_t)y * p.spitch + it.x0;
-                for (int c = 0; c < p.ncls; c++) {
-                    uint8_t *dst = a2ring + (size_t)(ag * TC_G + w) * p.a2_slot + c * 2048;
-                    const uint32_t *spc = p.sp[c];
-                    const float *pfc = p.pf[c];
+                // ALL global loads of the row first (both box sizes: up to 16 in flight per thread): the role is bound by their
+                // latency, one round trip per row instead of one per box size (or, with a branch in between, per load)
+                uint32_t wv[2][4];
+                float pw[2][4];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (c == 1 && p.ncls != 2) break;
+                    const uint32_t *spc = p.sp[c] + rowoff;
                     const int x_last = p.r_w - (c ? p.n_w2 : p.n_w);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int m = lane + 32 * i, gx = it.x0 + m;
+                        const bool ok = gx >= 1 && gx <= x_last && !(TC_EXP && (p.dbg_mode & 8));
+                        wv[c][i] = ok ? __ldg(spc + m) : (p.pack ? 0xFFFF0000u : 0u);
+                    }
+                }
+                if (!p.pack) {
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        if (c == 1 && p.ncls != 2) break;
+                        const float *pfc = p.pf[c] + rowoff;
+                        const int x_last = p.r_w - (c ? p.n_w2 : p.n_w);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int m = lane + 32 * i, gx = it.x0 + m;
+                            const bool ok = gx >= 1 && gx <= x_last && !(TC_EXP && (p.dbg_mode & 8));
+                            pw[c][i] = ok ? __ldg(pfc + m) : __int_as_float(0x7f800000);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (c == 1 && p.ncls != 2) break;
+                    uint8_t *dst = a2ring + (size_t)(ag * TC_G + w) * p.a2_slot + c * 2048;
                     const float bmax = p.bmax[c], amax = p.amax[c];
                     uint32_t sv[4];
                     float pv[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int m = lane + 32 * i, gx = it.x0 + m;
-                        const bool ok = gx >= 1 && gx <= x_last && !(TC_EXP && (p.dbg_mode & 8));
-                        sv[i] = ok ? __ldg(spc + rowoff + m) : 0u;
-                        pv[i] = ok ? __ldg(pfc + rowoff + m) : __int_as_float(0x7f800000);
+                        if (p.pack) {   // one word per window: s_p in the low half, norm_p in 11.5 fixed point in the high half
+                            sv[i] = wv[c][i] & 0xFFFFu;
+                            pv[i] = (wv[c][i] >> 16) == 0xFFFFu ? __int_as_float(0x7f800000) : (float)(wv[c][i] >> 16) * 0.03125f;
+                        } else {
+                            sv[i] = wv[c][i];
+                            pv[i] = pw[c][i];
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4 && !(TC_EXP && (p.dbg_mode & 32)); i++) {
@@ -1024,6 +1058,7 @@ struct CandArgs {
     int pitch, n_h, np;
     int n_w[2];              // box widths of the group (one or two box sizes of the same height)
     const uint32_t *sp[2];   // window-sum planes per box size
+    int pack;                // ... holding packed words: s_p is the low half
     int spitch;
     size_t plane_page_stride;
     double n_d[2], thr_d;
@@ -1054,7 +1089,8 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
             const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
             const TplInfo ti = a.tpl[t];
             const int bs = (int)ti.n_w == a.n_w[0] ? 0 : 1;   // which box size of the group
-            const uint32_t s_p = __ldg(a.sp[bs] + o);
+            const uint32_t s_pw = __ldg(a.sp[bs] + o);
+            const uint32_t s_p = a.pack ? (s_pw & 0xFFFFu) : s_pw;
             const int n_w = a.n_w[bs];
             uint32_t acc = 0, s2_p = 0;
             const int pitch4 = a.pitch >> 2;
@@ -1288,7 +1324,9 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.pf[0] = a.pf;
     p.sp[1] = tc.ncls == 2 ? a.sp2 : a.sp;
     p.pf[1] = tc.ncls == 2 ? a.pf2 : a.pf;
-    if (tc.ncls == 2 && (!a.sp2 || !a.pf2)) return cudaErrorInvalidValue;
+    p.pack = a.pack;
+    if (a.pack && tc.sshift) return cudaErrorInvalidValue;   // packed words need s_p < 2^16
+    if (tc.ncls == 2 && (!a.sp2 || (!a.pf2 && !a.pack))) return cudaErrorInvalidValue;
     p.spitch = a.spitch;
     p.plane_page_stride = a.plane_page_stride;
     p.cands = a.cands;
@@ -1425,6 +1463,7 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         ca.n_w[1] = tc.ncls == 2 ? tc.n_w2 : tc.n_w;
         ca.sp[0] = p.sp[0];
         ca.sp[1] = p.sp[1];
+        ca.pack = p.pack;
         ca.spitch = a.spitch;
         ca.plane_page_stride = a.plane_page_stride;
         ca.n_d[0] = (double)(ca.n_w[0] * tc.n_h);

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
             for (int y = 0; y < ny; y++, o += a.spitch, e_s += vp, e_q += vp) {
                 const uint32_t sp = e_s[w] - e_s[0];
                 const uint32_t s2 = e_q[w] - e_q[0];
-                sp_out[o] = sp;
+                if (!a.pack) sp_out[o] = sp;
                 if (extras && a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
                 // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
                 const unsigned long long vint = (unsigned long long)n_u * s2 - (unsigned long long)sp * sp;
@@ -175,7 +175,12 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
                 // (sqrt.approx: <= 2 ulp, i.e. < 2 units of the screen's 256-unit margin; the exact pass never reads pf)
                 float nrm;
                 asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nrm) : "f"((float)vint * inv_n_f));
-                pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : nrm;
+                if (a.pack) {   // s_p < 2^16 and norm_p < 2^11 for boxes of at most 256 pixels: one word, norm_p rounded to 1/32
+                    const uint32_t pfix = vint == 0ull ? 0xFFFFu : min(__float2uint_rn(nrm * 32.f), 0xFFFEu);
+                    sp_out[o] = sp | (pfix << 16);
+                } else {
+                    pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : nrm;
+                }
                 if (extras && a.rn) a.rn[o] = patch_rnorm(sp, s2, n_d);
             }
         };
