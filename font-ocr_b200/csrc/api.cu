@@ -495,7 +495,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     }
     CU(s.sel.ensure(PTR * g.sel_cap * 8));
     CU(s.ycut.ensure(PTR * 4));
-    CU(s.selcount.ensure(PTR * 4));
+    CU(s.selcount.ensure(PTR * 8));
     CU(s.flags.ensure(FLAG_BLOCKS * FLAG_WORDS * 4));
     unsigned int *const flags = s.flags.as<unsigned int>() + (size_t)flag_block * FLAG_WORDS;
 
@@ -506,7 +506,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     }
     c->launches++;
     CU(cudaMemsetAsync(s.rowcount.p, 0, PT * g.r_h * 4, st));
-    CU(cudaMemsetAsync(s.selcount.p, 0, PT * 4, st));
+    CU(cudaMemsetAsync(s.selcount.p, 0, PT * 8, st));
     CU(cudaMemsetAsync(flags, 0, FLAG_WORDS * 4, st));
 
     HitSink sink;

@@ -4,9 +4,11 @@
 //
 //   1. row_cut   : per (page, t) scan the per-row hit counts; y_cut = the row in which the
 //                  cumulative count reaches n_out (all rows if it never does).
-//   2. select    : keep only hits with y <= y_cut -- at most n_out-1 + (hits of one row) of them.
-//   3. sort_emit : per (page, t) bitonic sort of the 64-bit keys (y:16 | x:16 | sim bits:32) in
-//                  shared memory, write the first min(count, n_out) as Match{u16 x, u16 y, f32}.
+//   2. select    : keep only hits with y <= y_cut: those above the cut row (at most n_out-1) in one list, those
+//                  OF the cut row (at most one per x) in a second one.
+//   3. sort_emit : per (page, t) bitonic sorts of the 64-bit keys (y:16 | x:16 | sim bits:32) in shared memory --
+//                  the rows above the cut (a power of two <= n_out keys, not n_out + a row's worth rounded up) and
+//                  the cut row (a handful) -- then the first min(count, n_out) as Match{u16 x, u16 y, f32}.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -50,27 +52,28 @@ __global__ void __launch_bounds__(256) select_kernel(FinalizeArgs a)
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const Hit h = a.hits[i];
         const uint32_t pt = h.page * a.T + h.t;
-        const uint32_t y = h.yx >> 16;
-        if (y > a.y_cut[pt]) continue;
-        const unsigned slot = atomicAdd(a.sel_count + pt, 1u);
-        if (slot < a.sel_cap)
-            a.sel[(size_t)pt * a.sel_cap + slot] =
-                ((unsigned long long)h.yx << 32) | (unsigned long long)__float_as_uint(h.sim);
-        else
-            atomicExch(a.overflow, 1u);
+        const uint32_t y = h.yx >> 16, yc = a.y_cut[pt];
+        if (y > yc) continue;
+        const unsigned long long key = ((unsigned long long)h.yx << 32) | (unsigned long long)__float_as_uint(h.sim);
+        if (y < yc) {   // rows above the cut row: fewer than n_out hits by construction (all hits when there is no cut row)
+            const unsigned slot = atomicAdd(a.sel_count + pt, 1u);
+            if (slot < a.n_out)
+                a.sel[(size_t)pt * a.sel_cap + slot] = key;
+            else
+                atomicExch(a.overflow, 1u);
+        } else {        // the cut row itself: at most one hit per x
+            const unsigned slot = atomicAdd(a.sel_count + (size_t)a.n_pages * a.T + pt, 1u);
+            if (a.n_out + slot < a.sel_cap)
+                a.sel[(size_t)pt * a.sel_cap + a.n_out + slot] = key;
+            else
+                atomicExch(a.overflow, 1u);
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) sort_emit_kernel(FinalizeArgs a)
+// in-place ascending bitonic sort of keys[0 .. m), m a power of two (all threads of the block)
+__device__ __forceinline__ void bitonic_sort(unsigned long long *keys, uint32_t m)
 {
-    extern __shared__ __align__(16) unsigned long long keys[];
-    const uint32_t pt = blockIdx.x;
-    const uint32_t c = min(a.sel_count[pt], a.sel_cap);
-    uint32_t m = 1;
-    while (m < c) m <<= 1;
-    const unsigned long long *src = a.sel + (size_t)pt * a.sel_cap;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) keys[i] = i < c ? src[i] : ~0ull;
-    __syncthreads();
     for (uint32_t k = 2; k <= m; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
@@ -87,10 +90,29 @@ __global__ void __launch_bounds__(256) sort_emit_kernel(FinalizeArgs a)
             __syncthreads();
         }
     }
-    const uint32_t n = min(c, a.n_out);
+}
+
+__global__ void __launch_bounds__(256) sort_emit_kernel(FinalizeArgs a)
+{
+    extern __shared__ __align__(16) unsigned long long keys[];
+    const uint32_t pt = blockIdx.x;
+    const uint32_t c1 = min(a.sel_count[pt], a.n_out);                                   // above the cut row
+    const uint32_t c2 = min(a.sel_count[(size_t)a.n_pages * a.T + pt], a.sel_cap - a.n_out);   // the cut row
+    uint32_t m1 = 1, m2 = 1;
+    while (m1 < c1) m1 <<= 1;
+    while (m2 < c2) m2 <<= 1;
+    const unsigned long long *src = a.sel + (size_t)pt * a.sel_cap;
+    unsigned long long *keys2 = keys + m1;
+    for (uint32_t i = threadIdx.x; i < m1; i += blockDim.x) keys[i] = i < c1 ? src[i] : ~0ull;
+    for (uint32_t i = threadIdx.x; i < m2; i += blockDim.x) keys2[i] = i < c2 ? src[a.n_out + i] : ~0ull;
+    __syncthreads();
+    bitonic_sort(keys, m1);
+    if (c2 > 1) bitonic_sort(keys2, m2);
+    // every key of the cut row is larger than every key above it: the concatenation is the (y, x) raster order
+    const uint32_t n = min(c1 + c2, a.n_out);
     focr_match *out = a.out + (size_t)pt * a.n_out;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long k = keys[i];
+        const unsigned long long k = i < c1 ? keys[i] : keys2[i - c1];
         focr_match mt;
         mt.y = (uint16_t)(k >> 48);
         mt.x = (uint16_t)(k >> 32);
@@ -114,9 +136,13 @@ cudaError_t launch_finalize(const FinalizeArgs &a, cudaStream_t st, int *n_launc
     const int PT = a.n_pages * a.T;
     row_cut_kernel<<<(PT * 32 + 255) / 256, 256, 0, st>>>(a);
     select_kernel<<<148 * 8, 256, 0, st>>>(a);
-    cudaError_t e = cudaFuncSetAttribute(sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    cudaError_t e = cudaFuncSetAttribute(sort_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (4096 + 16384) * 8);
     if (e != cudaSuccess) return e;
-    sort_emit_kernel<<<PT, 256, (size_t)a.sel_cap * 8, st>>>(a);
+    // shared memory: the two sorted ranges, each rounded up to a power of two (<= pow2(n_out) + pow2(sel_cap - n_out) keys)
+    size_t m1 = 1, m2 = 1;
+    while (m1 < a.n_out) m1 <<= 1;
+    while (m2 < a.sel_cap - a.n_out) m2 <<= 1;
+    sort_emit_kernel<<<PT, 256, (m1 + m2) * 8, st>>>(a);
     if (n_launches) *n_launches += 3;
     return cudaGetLastError();
 }

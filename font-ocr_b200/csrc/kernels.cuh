@@ -68,8 +68,8 @@ struct FinalizeArgs {
     uint32_t hit_cap;
     const unsigned int *rowcount;   // [PT][r_h]
     uint32_t *y_cut;                // [PT]
-    unsigned int *sel_count;        // [PT]
-    unsigned long long *sel;        // [PT][sel_cap]
+    unsigned int *sel_count;        // [2][PT]: hits kept above the cut row / in the cut row
+    unsigned long long *sel;        // [PT][sel_cap]: [0, n_out) above the cut row, [n_out, sel_cap) the cut row
     uint32_t sel_cap;
     unsigned int *overflow;         // set when a selection list overflowed (cannot happen by construction)
     uint32_t T, r_h, n_pages, n_out;
