@@ -169,7 +169,9 @@ def test_decoded_text_identical(kctx, oracle, golden):
 
     letters = list(golden["text16_letters"])
     m, c = _scan(kctx, list(golden["text16_tpl"]), golden["text16_page"], 0.8)
-    ours = ncc.lines_to_text(ncc.process_hits(ncc.get_hits(m[0], c[0], letters)))
+    # the C++ host mirror (independent of the oracle's Python restatement; ncc.process_hits is its character-level twin)
+    ours = ncc.lines_to_text(ncc.host_process_hits(ncc.get_hits(m[0], c[0], letters)))
+    assert ours == ncc.lines_to_text(ncc.process_hits(ncc.get_hits(m[0], c[0], letters)))
     ref_hits = oracle.get_hits(golden["text16_page"], list(golden["text16_tpl"]), 0.8, "port")
     theirs = oracle.lines_to_text(oracle.process_hits(oracle.hits_with_letters(ref_hits, letters)))
     assert ours == theirs
