@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfocr_b200.so")
 STAMP = OUT + ".stamp"
-SOURCES = ["api.cu", "stats.cu", "scan_simt.cu", "scan_tc.cu", "finalize.cu", "postprocess.cu", "focr_decode.cu", "multi.cpp", "../host/focr_host.cpp"]
+SOURCES = ["api.cu", "stats.cu", "scan_simt.cu", "scan_tc.cu", "finalize.cu", "postprocess.cu", "focr_decode.cu", "multi.cpp", "../host/focr_host.cpp", "../host/focr_raster.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -32,7 +32,7 @@ NVCC_FLAGS = [
 def _digest() -> str:
     h = hashlib.sha256()
     files = sorted(os.listdir(CSRC)) + ["../../include/focr_b200.h", "../build.py", "../host/focr_host.cpp",
-                                        "../host/focr_host.hpp"]
+                                        "../host/focr_host.hpp", "../host/focr_raster.cpp"]
     for f in files:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):

@@ -392,3 +392,79 @@ class TemplateBank:
 
     def letters(self):
         return [t.letter for t in self.templates]
+
+
+# --------------------------------------------------------------------------- the C++ driver (host/focr_raster.cpp)
+def freetype_library_path() -> str:
+    """Path of the libfreetype the Python binding uses (Pillow's bundled one): what the C++ driver dlopens."""
+    import PIL
+
+    cands = glob.glob(os.path.join(os.path.dirname(PIL.__file__), "..", "pillow.libs", "libfreetype*.so*"))
+    if not cands:
+        raise OSError("Pillow's bundled libfreetype not found")
+    import PIL._imagingft  # noqa: F401  (pulls in libfreetype's own dependencies)
+
+    return os.path.realpath(cands[0])
+
+
+class NativeFont:
+    """focr_host_font: the C++ FreeType driver of libfocr_b200.so (same producers as this module, in C++)."""
+
+    def __init__(self, path: str | None = None):
+        from . import native
+
+        self.path = path or find_font()
+        self._h = C.c_void_p()
+        native.check(native.lib().focr_host_font_open(freetype_library_path().encode(), self.path.encode(), C.byref(self._h)))
+
+    def template_bank(self, size: float, alphabet: str = NCC_DEFAULT_ALPHABET, x_bits: int = 0, y_bits: int = 0,
+                      box_size: str = "alphabet", padding=(0, 0)):
+        """ncc.rs:587-640 in C++: ([u8 [n_h, n_w]] in (offset, letter) order, letters, corrected y offsets)."""
+        from . import native
+
+        lib = native.lib()
+        a = np.array([ord(c) for c in alphabet], np.uint32)
+        h = C.c_void_p()
+        native.check(lib.focr_host_tbank_render(self._h, C.c_float(size), native.ptr(a), len(a), x_bits, y_bits,
+                                                {"alphabet": 0, "font": 1, "char": 2}[box_size], padding[0], padding[1], C.byref(h)))
+        try:
+            n = int(lib.focr_host_tbank_count(h))
+            px = np.zeros(int(lib.focr_host_tbank_pixel_bytes(h)), np.uint8)
+            off, nw, nh = np.zeros(n, np.uint64), np.zeros(n, np.uint16), np.zeros(n, np.uint16)
+            let, cy = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+            native.check(lib.focr_host_tbank_get(h, native.ptr(px), native.ptr(off), native.ptr(nw), native.ptr(nh), native.ptr(let),
+                                                 native.ptr(cy)))
+        finally:
+            lib.focr_host_tbank_free(h)
+        tpls = [px[int(off[i]):int(off[i]) + int(nw[i]) * int(nh[i])].reshape(int(nh[i]), int(nw[i])).copy() for i in range(n)]
+        return tpls, [chr(c) for c in let], cy
+
+    def glyph_bank(self, size: float, alphabet: str = FOCR_DEFAULT_ALPHABET, kern_x: float = 1.0):
+        """focr's raster cache in C++: (pixels u8, rasters [n, 64] focr_glyph_raster, advance_px f32 [n], (origin_x, origin_y))."""
+        from . import native
+
+        lib = native.lib()
+        a = np.array([ord(c) for c in alphabet], np.uint32)
+        h = C.c_void_p()
+        native.check(lib.focr_host_gbank_render(self._h, C.c_float(size), native.ptr(a), len(a), C.c_float(kern_x), C.byref(h)))
+        try:
+            px = np.zeros(int(lib.focr_host_gbank_pixel_bytes(h)), np.uint8)
+            ras = np.zeros((len(a), 64), native.RASTER_DTYPE)
+            adv, org = np.zeros(len(a), np.float32), np.zeros(2, np.int32)
+            native.check(lib.focr_host_gbank_get(h, native.ptr(px), native.ptr(ras), native.ptr(adv), native.ptr(org)))
+        finally:
+            lib.focr_host_gbank_free(h)
+        return px, ras, adv, (int(org[0]), int(org[1]))
+
+    def close(self):
+        if self._h:
+            from . import native
+
+            native.lib().focr_host_font_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -273,6 +273,39 @@ int focr_host_line_text_with_spaces(const int32_t *xs, const uint32_t *letters, 
 int focr_host_search_c_u8(const uint8_t *gray, uint32_t r_w, uint32_t r_h, const uint8_t *needle, uint32_t n_w,
                           uint32_t n_h, float threshold, focr_match *out, uint32_t *n_out);
 
+/* ------------------------------------------------------------------------------------------
+ * Section 5 -- C++ FreeType driver (font-ocr_b200/host/focr_raster.cpp): the template and glyph-raster producers of the
+ * path's input side, i.e. the (glyph, subpixel shift) raster cache (README.md:44).  What a
+ * maintainer would call instead of re-rendering every template for every page (ncc.rs:561,631) and every glyph for every
+ * cell (main.rs:98-106).  freetype_so: path of a libfreetype shared object (opened with dlopen; there are no FreeType
+ * headers in this image).  Where the reference .unwrap()s a missing glyph the calls return FOCR_ERR_ARG with "panic: ...".
+ * PARITY UNPINNED for the rasters (font-kit / pathfinder semantics restated from memory); pinned byte for byte to the Python
+ * producer every test uses (tests/test_raster_native.py).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct focr_host_font focr_host_font;
+typedef struct focr_host_tbank focr_host_tbank;
+typedef struct focr_host_gbank focr_host_gbank;
+int focr_host_font_open(const char *freetype_so, const char *font_path, focr_host_font **out);
+void focr_host_font_close(focr_host_font *font);
+/* every template get_hits renders for one page (ncc.rs:587-640) in its iteration order (offset index, alphabet index);
+ * box_mode 0 = BoxSize::Alphabet (ncc.rs:600-626), 1 = Font (ncc.rs:589-599), 2 = Char (ncc.rs:627) */
+int focr_host_tbank_render(focr_host_font *font, float size, const uint32_t *alphabet, uint32_t n_alphabet, uint32_t x_bits,
+                           uint32_t y_bits, int box_mode, int pad_x, int pad_y, focr_host_tbank **out);
+uint32_t focr_host_tbank_count(const focr_host_tbank *bank);
+uint64_t focr_host_tbank_pixel_bytes(const focr_host_tbank *bank);
+/* the arrays focr_bank_create takes, plus the letters and the corrected y offsets --raw prints; any pointer may be NULL */
+int focr_host_tbank_get(const focr_host_tbank *bank, uint8_t *pixels, uint64_t *offsets, uint16_t *n_w, uint16_t *n_h,
+                        uint32_t *letters, float *corrected_y);
+void focr_host_tbank_free(focr_host_tbank *bank);
+/* focr's raster cache: 64 horizontal 26.6 phases per alphabet glyph + f32 advances -- the arrays focr_glyph_bank_create takes
+ * (rasters [n_alphabet][64], advance_px [n_alphabet], origin_xy = main.rs:147's origin) */
+int focr_host_gbank_render(focr_host_font *font, float size, const uint32_t *alphabet, uint32_t n_alphabet, float kern_x,
+                           focr_host_gbank **out);
+uint64_t focr_host_gbank_pixel_bytes(const focr_host_gbank *bank);
+int focr_host_gbank_get(const focr_host_gbank *bank, uint8_t *pixels, focr_glyph_raster *rasters, float *advance_px,
+                        int32_t *origin_xy);
+void focr_host_gbank_free(focr_host_gbank *bank);
+
 #ifdef __cplusplus
 }
 #endif
