@@ -168,17 +168,20 @@ __global__ void __launch_bounds__(ST_THREADS) window_stats_kernel(StatsArgs a)
                 const uint32_t s2 = e_q[w] - e_q[0];
                 if (!a.pack) sp_out[o] = sp;
                 if (extras && a.s2p) a.s2p[o] = s2;   // only the SIMT scan and the parity probe read it
-                // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
-                const unsigned long long vint = (unsigned long long)n_u * s2 - (unsigned long long)sp * sp;
-                // prefilter operand of the tcgen05 epilogue: norm_p = sqrt(vint/n); +inf marks a
-                // constant window (rnorm_p = inf in the reference -> never a hit)
-                // (sqrt.approx: <= 2 ulp, i.e. < 2 units of the screen's 256-unit margin; the exact pass never reads pf)
-                float nrm;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nrm) : "f"((float)vint * inv_n_f));
-                if (a.pack) {   // s_p < 2^16 and norm_p < 2^11 for boxes of at most 256 pixels: one word, norm_p rounded to 1/32
-                    const uint32_t pfix = vint == 0ull ? 0xFFFFu : min(__float2uint_rn(nrm * 32.f), 0xFFFEu);
+                if (a.pack) {   // boxes of at most 256 pixels: n*s2 and sp^2 fit 32 bits, s_p 16, norm_p 11 -> ONE word per window
+                    const uint32_t v32 = n_u * s2 - sp * sp;        // n*norm2_p, an exact non-negative integer; 0 <=> constant window
+                    float nrm;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nrm) : "f"((float)v32 * inv_n_f));
+                    const uint32_t pfix = v32 == 0u ? 0xFFFFu : min(__float2uint_rn(nrm * 32.f), 0xFFFEu);   // norm_p rounded to 1/32
                     sp_out[o] = sp | (pfix << 16);
                 } else {
+                    // n*norm2_p = n*s2 - sp^2 is an exact non-negative integer (< 2^45)
+                    const unsigned long long vint = (unsigned long long)n_u * s2 - (unsigned long long)sp * sp;
+                    // prefilter operand of the tcgen05 epilogue: norm_p = sqrt(vint/n); +inf marks a
+                    // constant window (rnorm_p = inf in the reference -> never a hit)
+                    // (sqrt.approx: <= 2 ulp, i.e. < 2 units of the screen's 256-unit margin; the exact pass never reads pf)
+                    float nrm;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(nrm) : "f"((float)vint * inv_n_f));
                     pf_out[o] = vint == 0ull ? __int_as_float(0x7f800000) : nrm;
                 }
                 if (extras && a.rn) a.rn[o] = patch_rnorm(sp, s2, n_d);

@@ -417,6 +417,9 @@ def test_multi_device_scan_identical_to_single(ctx, oracle):
     tpls = [rng.integers(0, 256, (40, 20), dtype=np.uint8) for _ in range(5)] + \
            [rng.integers(0, 256, (14, 15), dtype=np.uint8) for _ in range(70)]
     bank1 = ncc.Bank(ctx, tpls)
+    every = ncc.MultiContext()   # devices == NULL, n_devices == 0: one context per visible GPU
+    assert every.size == n_gpu
+    every.close()
     mctx = ncc.MultiContext(devices=devices)
     try:
         assert mctx.size == len(devices)
