@@ -2,6 +2,7 @@
 // batched scan pipeline (H2D -> stage -> stats -> scan -> finalize -> D2H) and the compat shim that
 // exports the reference's own `ncc_8_u8` / `ncc_16_u8` symbols (ncc.cpp:48-63, 253-268).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -732,14 +733,21 @@ static bool host_ptr_is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+// Host threads per staging copy: the hardware threads, at most 8, shared between the GPUs that stage at the same time --
+// the ranks torchrun placed on this host (LOCAL_WORLD_SIZE) or the devices of a focr_multi call in flight.
+static std::atomic<int> g_stage_sharers{1};
+void focr_internal_stage_sharers(int n) { g_stage_sharers.store(n < 1 ? 1 : n); }
 static int stage_threads()
 {
-    static const int n = [] {
-        if (const char *e = getenv("FOCR_STAGE_THREADS")) return std::max(1, std::min(16, atoi(e)));
-        const unsigned hc = std::thread::hardware_concurrency();
-        return (int)std::max(1u, std::min(4u, hc / 2));
+    static const int base = [] {
+        if (const char *e = getenv("FOCR_STAGE_THREADS")) return -std::max(1, std::min(16, atoi(e)));   // explicit: not divided
+        const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        return (int)std::max(1u, std::min(8u, hc / (unsigned)ranks));
     }();
-    return n;
+    if (base < 0) return -base;
+    return std::max(1, base / g_stage_sharers.load());
 }
 
 // rows x row_bytes from src (stride src_stride) to dst (stride dst_stride), split over the staging threads
@@ -838,17 +846,21 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
             CU(s.out.ensure((size_t)Bres * T * n_out * sizeof(focr_match)));
             CU(s.counts.ensure((size_t)Bres * T * 4));
             const uint8_t *src = pages_host + (size_t)p0 * page_stride;
-            size_t src_stride = page_stride;
             if (stage_in) {
+                // pageable pages: host threads copy a few pages into the slot's pinned staging, their DMA starts at once
+                // and runs while the next few are being copied (copy-in and H2D of a chunk overlap, not add up)
                 CU(s.gray_pin.ensure(page_bytes * Bres));
-                parallel_copy(s.gray_pin.as<uint8_t>(), page_bytes, src, page_stride, page_bytes, nB);
-                src = s.gray_pin.as<uint8_t>();
-                src_stride = page_bytes;
-            }
-            if (src_stride == page_bytes) {
+                const uint32_t sub = std::max<uint32_t>(1, (uint32_t)((32u << 20) / std::max<size_t>(page_bytes, 1)));
+                for (uint32_t q0 = 0; q0 < nB; q0 += sub) {
+                    const uint32_t nq = std::min(sub, nB - q0);
+                    uint8_t *pin = s.gray_pin.as<uint8_t>() + (size_t)q0 * page_bytes;
+                    parallel_copy(pin, page_bytes, src + (size_t)q0 * page_stride, page_stride, page_bytes, nq);
+                    CU(cudaMemcpyAsync(s.gray.as<uint8_t>() + (size_t)q0 * page_bytes, pin, page_bytes * nq, cudaMemcpyHostToDevice, c->h2d));
+                }
+            } else if (page_stride == page_bytes) {
                 CU(cudaMemcpyAsync(s.gray.p, src, page_bytes * nB, cudaMemcpyHostToDevice, c->h2d));
             } else {
-                CU(cudaMemcpy2DAsync(s.gray.p, page_bytes, src, src_stride, page_bytes, nB, cudaMemcpyHostToDevice, c->h2d));
+                CU(cudaMemcpy2DAsync(s.gray.p, page_bytes, src, page_stride, page_bytes, nB, cudaMemcpyHostToDevice, c->h2d));
             }
             CU(cudaEventRecord(s.ev_h2d, c->h2d));
             CU(cudaStreamWaitEvent(c->stream, s.ev_h2d, 0));

@@ -14,6 +14,7 @@
 #include "../../include/focr_b200.h"
 
 int focr_internal_fail(int code, const std::string &msg);   // api.cu: sets the calling thread's focr_last_error()
+void focr_internal_stage_sharers(int n);                    // api.cu: how many GPUs share the host's staging threads right now
 
 struct focr_multi {
     std::vector<focr_ctx *> ctx;
@@ -145,12 +146,15 @@ extern "C" int focr_multi_ncc_scan(focr_multi *m, const focr_multi_bank *b, cons
         return focr_internal_fail(FOCR_ERR_ARG, "focr_multi_ncc_scan: NULL argument, foreign bank or no pages");
     const uint32_t n_dev = (uint32_t)std::min<size_t>(m->ctx.size(), n_pages);
     const size_t T = b->T;
-    return for_each_device(n_dev, [&](uint32_t i) {
+    focr_internal_stage_sharers((int)n_dev);   // pageable callers: the devices share the host's staging threads
+    const int rc = for_each_device(n_dev, [&](uint32_t i) {
         uint32_t p0, np;
         block_of(n_pages, i, n_dev, p0, np);
         return focr_ncc_scan(m->ctx[i], b->bank[i], pages_host + (size_t)p0 * page_stride, page_stride, r_w, r_h, np, threshold,
                              n_out, out_host + (size_t)p0 * T * n_out, counts_host + (size_t)p0 * T);
     });
+    focr_internal_stage_sharers(1);
+    return rc;
 }
 
 extern "C" int focr_multi_glyph_bank_create(focr_multi *m, const uint8_t *pixels, size_t n_pixel_bytes,
