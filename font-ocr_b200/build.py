@@ -32,7 +32,7 @@ NVCC_FLAGS = [
 def _digest() -> str:
     h = hashlib.sha256()
     files = sorted(os.listdir(CSRC)) + ["../../include/focr_b200.h", "../build.py", "../host/focr_host.cpp",
-                                        "../host/focr_host.hpp", "../host/focr_raster.cpp"]
+                                        "../host/focr_host.hpp", "../host/focr_raster.cpp", "../host/focr_cli.cpp"]
     for f in files:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):
@@ -66,7 +66,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(r.stderr)
     open(stamp, "w").write(dg)
+    if not exp and not variant:
+        build_cli(out)
     return out
+
+
+def build_cli(lib: str) -> str:
+    """The C++ front-end font-ocr_b200/bin/focr_cli (host/focr_cli.cpp): plain g++, linked against the library next to it."""
+    cli = os.path.join(HERE, "bin", "focr_cli")
+    os.makedirs(os.path.dirname(cli), exist_ok=True)
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", os.path.join(HERE, "host", "focr_cli.cpp"), "-o", cli,
+           "-L" + HERE, "-l:" + os.path.basename(lib), "-lz", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building focr_cli")
+    return cli
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@
 // There are no FreeType headers in this image: the library (any libfreetype.so.6; the tests pass Pillow's bundled one) is
 // opened with dlopen and the handful of public structs used here are declared below exactly as <freetype/freetype.h>
 // declares them for LP64.
+#include <dirent.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -206,6 +207,25 @@ extern "C" int focr_host_font_open(const char *freetype_so, const char *font_pat
     focr_host_font *f = new focr_host_font();
     f->ft.so = dlopen(freetype_so, RTLD_NOW | RTLD_LOCAL);
     if (!f->ft.so) {
+        // a bundled FreeType (e.g. Pillow's) keeps its own dependencies (libpng, libbrotli) next to it without an rpath: load
+        // the directory's other libraries first (a few passes: they depend on each other), then try again
+        const std::string path = freetype_so;
+        const size_t slash = path.rfind('/');
+        if (slash != std::string::npos) {
+            const std::string dir = path.substr(0, slash);
+            for (int pass = 0; pass < 3; pass++)
+                if (DIR *d = opendir(dir.c_str())) {
+                    while (dirent *e = readdir(d)) {
+                        const std::string name = e->d_name;
+                        if (name.rfind("lib", 0) == 0 && name.find(".so") != std::string::npos && dir + "/" + name != path)
+                            dlopen((dir + "/" + name).c_str(), RTLD_LAZY | RTLD_GLOBAL);
+                    }
+                    closedir(d);
+                }
+            f->ft.so = dlopen(freetype_so, RTLD_NOW | RTLD_LOCAL);
+        }
+    }
+    if (!f->ft.so) {
         const std::string why = dlerror();
         delete f;
         return focr_internal_fail(FOCR_ERR_ARG, "focr_host_font_open: dlopen(" + std::string(freetype_so) + "): " + why);
@@ -233,6 +253,22 @@ extern "C" int focr_host_font_open(const char *freetype_so, const char *font_pat
     f->bounding_box = RectF{(float)bb.xMin, (float)bb.yMin, (float)bb.xMax, (float)bb.yMax};
     f->reset_size();
     *out = f;
+    return FOCR_OK;
+}
+
+// per-letter metrics in pixels at `size`: the left bearing --raw prints (ncc.rs:683-698: typographic_bounds().origin_x() * to_px)
+// and the pen advance (advance / units_per_em * size, f32 in that order, main.rs:176-178)
+extern "C" int focr_host_font_glyph_metrics(focr_host_font *f, uint32_t letter, float size, float *bearing_x_px, float *advance_px)
+{
+    if (!f || !bearing_x_px || !advance_px) return focr_internal_fail(FOCR_ERR_ARG, "focr_host_font_glyph_metrics: NULL argument");
+    unsigned gid;
+    if (!f->glyph_for_char(letter, gid)) return focr_internal_fail(FOCR_ERR_ARG, "panic: no glyph for U+" + std::to_string(letter));
+    RectF tb;
+    float ax;
+    if (!f->typographic_bounds(gid, tb) || !f->advance(gid, ax)) return focr_internal_fail(FOCR_ERR_ARG, "FT_Load_Glyph failed");
+    const float to_px = (1.0f / (float)f->units_per_em) * size;
+    *bearing_x_px = tb.x0 * to_px;
+    *advance_px = (ax / (float)f->units_per_em) * size;
     return FOCR_OK;
 }
 

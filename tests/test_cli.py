@@ -38,6 +38,43 @@ def test_load_luma8_gray_and_rec709(pkg, tmp_path):
     assert got[0, :4].tolist() == [0, 0, 1, 255]
 
 
+def _cpp_cli(built_lib):
+    import os
+
+    return os.path.join(os.path.dirname(built_lib), "bin", "focr_cli")
+
+
+def test_cpp_cli_decodes_images_like_the_python_front_end(built_lib, pkg, tmp_path):
+    """host/focr_cli.cpp decodes PNG (through zlib) and PNM itself: `into_luma8()` must give the same bytes as cli.load_luma8
+    for gray / RGB / RGBA / palette / 16-bit PNGs and binary PGM / PPM."""
+    import io
+    import subprocess
+
+    from PIL import Image
+
+    from font_ocr_b200.cli import load_luma8
+
+    rng = np.random.default_rng(8)
+    g = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    g16 = rng.integers(0, 65536, (37, 53), dtype=np.uint16)
+    files = {}
+    Image.fromarray(g).save(tmp_path / "g.png"); files["g.png"] = None
+    Image.fromarray(rgb).save(tmp_path / "c.png"); files["c.png"] = None
+    Image.fromarray(rgba).save(tmp_path / "a.png"); files["a.png"] = None
+    Image.fromarray(g16).save(tmp_path / "g16.png"); files["g16.png"] = None
+    Image.fromarray(rgb).convert("P", palette=Image.ADAPTIVE, colors=64).save(tmp_path / "p.png"); files["p.png"] = None
+    Image.fromarray((g > 127).astype(np.uint8) * 255).convert("1").save(tmp_path / "b.png"); files["b.png"] = None
+    Image.fromarray(g).save(tmp_path / "g.pgm"); files["g.pgm"] = None
+    Image.fromarray(rgb).save(tmp_path / "c.ppm"); files["c.ppm"] = None
+    for name in files:
+        out = subprocess.run([_cpp_cli(built_lib), "luma", str(tmp_path / name)], capture_output=True, check=True).stdout
+        got = np.asarray(Image.open(io.BytesIO(out)))
+        exp = load_luma8(str(tmp_path / name))
+        assert got.shape == exp.shape and np.array_equal(got, exp), name
+
+
 def test_flags_mirror_the_reference(pkg):
     from font_ocr_b200 import cli
 
@@ -119,3 +156,44 @@ def test_focr_cli(built_lib, oracle, font, pkg, tmp_path):
     assert cli.focr_main(["-i"] + paths + ["-f", font.path, "-t", "13", "-x", "45", "-y", "39", "-w", "608",
                                             "--line-height", "12", "--line-advance", "15", "--batch", "2"], out=buf) == 0
     assert buf.getvalue().splitlines() == exp and len(exp) >= 9
+
+
+@pytest.mark.gpu
+def test_cpp_cli_prints_what_the_python_front_end_prints(built_lib, font, pkg, tmp_path):
+    """host/focr_cli.cpp (C++ FreeType driver, PNG/PNM decoding, C++ process_hits) against font-ocr_b200/cli.py (Python
+    producers, device process_hits): identical stdout for `ncc` text / --csv / --raw / --spaces and for `focr`."""
+    import subprocess
+
+    from PIL import Image
+
+    from font_ocr_b200 import cli
+
+    exe, ft = _cpp_cli(built_lib), pkg.raster.freetype_library_path()
+    bank_h = pkg.raster.TemplateBank(font, 13, x_bits=1)
+    paths = []
+    for i, (w, h, seed) in enumerate(((608, 300, 11), (500, 260, 12), (608, 300, 13))):
+        paths.append(str(tmp_path / (f"p{i}.png" if i != 1 else "p1.pgm")))
+        Image.fromarray(pkg.pages.make_ncc_page(bank_h, w, h, seed=seed, shifts="bank")[0]).save(paths[-1])
+    base = ["-f", font.path, "-t", "13", "--x-bits", "1"]
+
+    def both(sub, args):
+        buf = io.StringIO()
+        assert (cli.ncc_main if sub == "ncc" else cli.focr_main)(args, out=buf) == 0
+        r = subprocess.run([exe, sub] + args + ["--freetype", ft], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return buf.getvalue(), r.stdout
+
+    for extra in ([], ["--csv"], ["--spaces"], ["--threshold", "0.7", "--anchor-threshold", "0.9", "--overlap", "3"]):
+        py, cpp = both("ncc", ["-i"] + paths + base + extra)
+        assert py == cpp and len(py.splitlines()) > 4, extra
+    py, cpp = both("ncc", ["-i", paths[0]] + base + ["--raw"])
+    assert py == cpp and len(py.splitlines()) > 100
+    fpaths = []
+    for i, seed in enumerate((21, 22)):
+        fpaths.append(str(tmp_path / f"f{i}.png"))
+        Image.fromarray(pkg.pages.make_focr_page(font, 13, 700, 39 + 15 * 4 + 20, seed=seed, fill=1.0)[0]).save(fpaths[-1])
+    py, cpp = both("focr", ["-i"] + fpaths + ["-f", font.path, "-t", "13", "-x", "45", "-y", "39", "-w", "608", "--line-height", "12",
+                                               "--line-advance", "15"])
+    assert py == cpp and len(py.splitlines()) >= 6
+    # refused flags are refused by both, never silently different
+    assert subprocess.run([exe, "ncc", "-i", paths[0]] + base + ["--rust"], capture_output=True).returncode == 2
