@@ -52,6 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     stamp = out + ".stamp"
     dg = _digest() + ("+exp" if exp else "") + variant
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dg:
+        if not exp and not variant and not os.path.exists(os.path.join(HERE, "bin", "focr_cli")):
+            build_cli(out)
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = ["-DFOCR_TC_EXPERIMENTS"] if exp else []  # tools/tc_trace.py, tools/tc_modes.py, tools/tc_timeline.py
