@@ -9,7 +9,7 @@ main.rs:342-385 and main.rs:387-470.  Differences, all deliberate:
   * pages of one run are scanned as batches on the GPU instead of one rayon task each; output order is by page index
     either way (ncc.rs:847, main.rs:468);
   * a page without any anchor line prints nothing, where the reference panics (ncc.rs:1040);
-  * `--hinting`, `--rust`, `--test`, `--verify` are refused: hinted rasters, the scalar fallback (numerically different,
+  * `--rust`, `--test`, `--verify` are refused: the scalar fallback (numerically different,
     SURVEY K9) and the diagnostics images are outside the hot path.
 All compute happens in libfocr_b200.so; there is no CPU path here.
 """
@@ -130,8 +130,8 @@ def ncc_raw_lines(bank: raster.TemplateBank, matches: np.ndarray, counts: np.nda
 def ncc_main(argv=None, out=None) -> int:
     args = _ncc_parser().parse_args(argv)
     out = out or sys.stdout
-    if args.hinting or args.rust:
-        sys.stderr.write("ncc: --hinting / --rust are not supported by the B200 path (DESIGN.md section 7)\n")
+    if args.rust:
+        sys.stderr.write("ncc: --rust is not supported by the B200 path (DESIGN.md section 7)\n")
         return 2
     if args.raw and len(args.img) != 1:
         raise AssertionError("--raw takes exactly one image (ncc.rs:833-837)")
@@ -139,7 +139,7 @@ def ncc_main(argv=None, out=None) -> int:
 
     from . import ncc
 
-    font = raster.Font(args.font)
+    font = raster.Font(args.font, hinting=args.hinting)
     bank_h = raster.TemplateBank(font, args.text_size, args.alphabet, args.x_bits, args.y_bits, args.box_size,
                                  (args.x_padding, args.y_padding))
     if args.verbose:
@@ -235,12 +235,12 @@ def _focr_parser():
 def focr_main(argv=None, out=None) -> int:
     args = _focr_parser().parse_args(argv)
     out = out or sys.stdout
-    if args.hinting or args.test or args.verify:
-        sys.stderr.write("focr: --hinting / --test / --verify are not supported by the B200 path (DESIGN.md section 7)\n")
+    if args.test or args.verify:
+        sys.stderr.write("focr: --test / --verify are not supported by the B200 path (DESIGN.md section 7)\n")
         return 2
     from . import focr, ncc
 
-    font = raster.Font(args.font)
+    font = raster.Font(args.font, hinting=args.hinting)
     images = [load_luma8(p) for p in args.img]
     ctx = ncc.Context(args.device)
     bank = focr.GlyphBank(ctx, font, args.text_size, args.alphabet, args.kerning)

@@ -8,7 +8,7 @@
 // scan / decode the pages in GPU batches (focr_ncc_scan / focr_decode_pages), run process_hits (focr_host.cpp) and print in
 // the reference's formats.  Same output as the Python front-end font-ocr_b200/cli.py (tests/test_cli.py compares them).
 // Extensions are opt-in and named as such: --spaces, --space-advance, --max-matches, --device, --batch, --freetype.
-// --hinting, --rust, --test, --verify are refused, never silently different.
+// --rust, --test, --verify are refused, never silently different.
 #include <zlib.h>
 
 #include <algorithm>
@@ -300,8 +300,8 @@ int ncc_main(int argc, char **argv)
                           {"--x-padding", "0"}, {"--y-padding", "0"}, {"--device", "0"}, {"--batch", "16"}, {"--max-matches", "1024"},
                           {"--space-advance", ""}, {"--freetype", ""}},
                          {"--hinting", "--rust", "--csv", "--raw", "--verbose", "--spaces", "--save-letters"}, {"--font", "--text-size"});
-    if (a.on("--hinting") || a.on("--rust")) {
-        fprintf(stderr, "ncc: --hinting / --rust are not supported by the B200 path (DESIGN.md section 7)\n");
+    if (a.on("--rust")) {
+        fprintf(stderr, "ncc: --rust is not supported by the B200 path (DESIGN.md section 7)\n");
         return 2;
     }
     if (a.on("--raw") && a.img.size() != 1) die("--raw takes exactly one image (ncc.rs:833-837)");
@@ -314,6 +314,7 @@ int ncc_main(int argc, char **argv)
 
     focr_host_font *font = nullptr;
     CHECK(focr_host_font_open(freetype_path(a).c_str(), a.s("--font").c_str(), &font));
+    focr_host_font_set_hinting(font, a.on("--hinting"));   // HintingOptions::Full(text_size), ncc.rs:547-551
     focr_host_tbank *tb = nullptr;
     CHECK(focr_host_tbank_render(font, size, alpha.data(), (uint32_t)alpha.size(), xb, yb, modes.at(a.s("--box-size")),
                                  (int)a.i("--x-padding"), (int)a.i("--y-padding"), &tb));
@@ -421,14 +422,15 @@ int focr_main(int argc, char **argv)
                           {"--width", ""}, {"--line-height", ""}, {"--line-advance", ""}, {"--test", ""}, {"--verify", ""}, {"--device", "0"},
                           {"--batch", "16"}, {"--freetype", ""}},
                          {"--hinting"}, {"--font", "--text-size", "--width", "--line-height", "--line-advance"});
-    if (a.on("--hinting") || a.has("--test") || a.has("--verify")) {
-        fprintf(stderr, "focr: --hinting / --test / --verify are not supported by the B200 path (DESIGN.md section 7)\n");
+    if (a.has("--test") || a.has("--verify")) {
+        fprintf(stderr, "focr: --test / --verify are not supported by the B200 path (DESIGN.md section 7)\n");
         return 2;
     }
     const std::u32string alphabet = utf8_to_u32(a.s("--alphabet"));
     std::vector<uint32_t> alpha(alphabet.begin(), alphabet.end());
     focr_host_font *font = nullptr;
     CHECK(focr_host_font_open(freetype_path(a).c_str(), a.s("--font").c_str(), &font));
+    focr_host_font_set_hinting(font, a.on("--hinting"));   // HintingOptions::Full(text_size), main.rs:394-398
     focr_host_gbank *gb = nullptr;
     CHECK(focr_host_gbank_render(font, (float)a.f("--text-size"), alpha.data(), (uint32_t)alpha.size(), (float)a.f("--kerning"), &gb));
     std::vector<uint8_t> px(focr_host_gbank_pixel_bytes(gb));

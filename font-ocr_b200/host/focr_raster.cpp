@@ -105,6 +105,7 @@ struct focr_host_font {
     FtApi ft;
     FT_FaceRec *face = nullptr;
     unsigned units_per_em = 0;
+    bool hinting = false;   // --hinting = HintingOptions::Full: rasterise with FT_LOAD_TARGET_NORMAL instead of FT_LOAD_NO_HINTING
     float ascent = 0;
     RectF bounding_box;
     std::map<unsigned, RectF> tb_cache;
@@ -155,7 +156,7 @@ struct focr_host_font {
         FT_Matrix mat{0x10000, 0, 0, 0x10000};
         FT_Vector delta{dx26, dy26};
         ft.Set_Transform(face, &mat, &delta);
-        const int rc = ft.Load_Glyph(face, gid, FT_LOAD_DEFAULT | FT_LOAD_RENDER | FT_LOAD_NO_HINTING);
+        const int rc = ft.Load_Glyph(face, gid, FT_LOAD_DEFAULT | FT_LOAD_RENDER | (hinting ? 0 : FT_LOAD_NO_HINTING));
         bool ok = rc == 0;
         if (ok) {
             const FT_GlyphSlotRec *slot = face->glyph;
@@ -270,6 +271,12 @@ extern "C" int focr_host_font_glyph_metrics(focr_host_font *f, uint32_t letter, 
     *bearing_x_px = tb.x0 * to_px;
     *advance_px = (ax / (float)f->units_per_em) * size;
     return FOCR_OK;
+}
+
+// the reference's --hinting (HintingOptions::Full(size), ncc.rs:547-551, main.rs:394-398): hinted rasters; metrics stay unhinted
+extern "C" void focr_host_font_set_hinting(focr_host_font *f, int on)
+{
+    if (f) f->hinting = on != 0;
 }
 
 extern "C" void focr_host_font_close(focr_host_font *f)

@@ -30,7 +30,7 @@ SYMBOLS = [
     "focr_ncc_scan", "focr_ncc_scan_device", "focr_process_hits_device", "focr_window_stats", "focr_ncc_numerators",
     "focr_glyph_bank_create", "focr_glyph_bank_destroy", "focr_decode_pages", "focr_sum_of_squares",
     "focr_host_process_hits", "focr_host_search_c_u8", "focr_host_line_text_with_spaces",
-    "focr_host_font_open", "focr_host_font_close", "focr_host_font_glyph_metrics", "focr_host_tbank_render", "focr_host_tbank_count", "focr_host_tbank_pixel_bytes",
+    "focr_host_font_open", "focr_host_font_close", "focr_host_font_set_hinting", "focr_host_font_glyph_metrics", "focr_host_tbank_render", "focr_host_tbank_count", "focr_host_tbank_pixel_bytes",
     "focr_host_tbank_get", "focr_host_tbank_free", "focr_host_gbank_render", "focr_host_gbank_pixel_bytes", "focr_host_gbank_get",
     "focr_host_gbank_free",
 ]
@@ -107,6 +107,8 @@ def lib():
     l.focr_host_line_text_with_spaces.argtypes = [vp, vp, u32, vp, vp, u32, C.c_float, vp, u32, vp]
     l.focr_host_font_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
     l.focr_host_font_glyph_metrics.argtypes = [vp, u32, C.c_float, vp, vp]
+    l.focr_host_font_set_hinting.argtypes = [vp, C.c_int]
+    l.focr_host_font_set_hinting.restype = None
     l.focr_host_font_close.argtypes = [vp]
     l.focr_host_font_close.restype = None
     l.focr_host_tbank_render.argtypes = [vp, C.c_float, vp, u32, u32, u32, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]

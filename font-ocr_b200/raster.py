@@ -206,9 +206,12 @@ def _trunc_26_6(v) -> int:
 class Font:
     """The subset of font_kit::loaders::freetype::Font the hot path calls."""
 
-    def __init__(self, path: str | None = None, face_index: int = 0):
+    def __init__(self, path: str | None = None, face_index: int = 0, hinting: bool = False):
+        """hinting: the reference's --hinting = HintingOptions::Full(size) (ncc.rs:547-551, main.rs:394-398): font-kit then
+        rasterises with FT_LOAD_TARGET_NORMAL instead of FT_LOAD_NO_HINTING (metrics stay unhinted font units)."""
         ft, lib = _freetype()
         self._ft = ft
+        self.hinting = bool(hinting)
         self.path = path or find_font()
         face = C.POINTER(_FT_FaceRec)()
         if ft.FT_New_Face(lib, self.path.encode(), face_index, C.byref(face)) != 0:
@@ -275,7 +278,7 @@ class Font:
         delta = _FT_Vector(dx_26_6, dy_26_6)
         ft.FT_Set_Transform(self._face, C.byref(mat), C.byref(delta))
         try:
-            if ft.FT_Load_Glyph(self._face, gid, FT_LOAD_DEFAULT | FT_LOAD_RENDER | FT_LOAD_NO_HINTING) != 0:
+            if ft.FT_Load_Glyph(self._face, gid, FT_LOAD_DEFAULT | FT_LOAD_RENDER | (0 if self.hinting else FT_LOAD_NO_HINTING)) != 0:
                 raise OSError("FT_Load_Glyph(render) failed")
             slot = self._face.contents.glyph.contents
             b = slot.bitmap
@@ -410,12 +413,13 @@ def freetype_library_path() -> str:
 class NativeFont:
     """focr_host_font: the C++ FreeType driver of libfocr_b200.so (same producers as this module, in C++)."""
 
-    def __init__(self, path: str | None = None):
+    def __init__(self, path: str | None = None, hinting: bool = False):
         from . import native
 
         self.path = path or find_font()
         self._h = C.c_void_p()
         native.check(native.lib().focr_host_font_open(freetype_library_path().encode(), self.path.encode(), C.byref(self._h)))
+        native.lib().focr_host_font_set_hinting(self._h, int(bool(hinting)))
 
     def template_bank(self, size: float, alphabet: str = NCC_DEFAULT_ALPHABET, x_bits: int = 0, y_bits: int = 0,
                       box_size: str = "alphabet", padding=(0, 0)):

@@ -287,6 +287,8 @@ typedef struct focr_host_tbank focr_host_tbank;
 typedef struct focr_host_gbank focr_host_gbank;
 int focr_host_font_open(const char *freetype_so, const char *font_path, focr_host_font **out);
 void focr_host_font_close(focr_host_font *font);
+/* the reference's --hinting (HintingOptions::Full, ncc.rs:547-551, main.rs:394-398): later banks are rasterised hinted */
+void focr_host_font_set_hinting(focr_host_font *font, int on);
 /* per-letter metrics in pixels at `size`: the left bearing --raw prints (ncc.rs:683-698) and the f32 pen advance (main.rs:176-178) */
 int focr_host_font_glyph_metrics(focr_host_font *font, uint32_t letter, float size, float *bearing_x_px, float *advance_px);
 /* every template get_hits renders for one page (ncc.rs:587-640) in its iteration order (offset index, alphabet index);

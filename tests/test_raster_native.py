@@ -50,3 +50,23 @@ def test_glyph_bank_identical_to_python(nfont, pkg, font, oracle):
             assert (a["left"], a["top"], a["w"], a["h"]) == (b["left"], b["top"], b["w"], b["h"]), (g, ph)
             n = int(a["w"]) * int(a["h"])
             assert np.array_equal(px[int(a["offset"]):int(a["offset"]) + n], cache.pixels[int(b["offset"]):int(b["offset"]) + n])
+
+
+def test_hinted_banks_identical_and_phase_property(built_lib, pkg, font):
+    """--hinting (HintingOptions::Full, ncc.rs:547-551): both producers rasterise with FT_LOAD_TARGET_NORMAL; the banks stay
+    byte-identical to each other, and a hinted bitmap still only depends on the 26.6 phase of
+    the pen delta (FreeType applies the transform after hinting) -- what the (glyph, phase) cache relies on."""
+    hfont = pkg.raster.Font(font.path, hinting=True)
+    nfont = pkg.raster.NativeFont(font.path, hinting=True)
+    ref = pkg.raster.TemplateBank(hfont, 13, x_bits=1)
+    tpls, letters, _ = nfont.template_bank(13, pkg.raster.NCC_DEFAULT_ALPHABET, 1, 0)
+    assert all(np.array_equal(a, t.pixels) for a, t in zip(tpls, ref.templates)) and len(tpls) == len(ref)
+    # (whether hinted rasters differ from unhinted ones depends on the font: the Lato web font of this image carries no
+    # instructions and its rasters come out the same)
+    for ch in "AgW/":
+        gid = hfont.glyph_for_char(ch)
+        for frac in (0, 17, 63):
+            b0, l0, t0 = hfont.glyph_bitmap(gid, 13, frac, -10 * 64)
+            b1, l1, t1 = hfont.glyph_bitmap(gid, 13, frac + 64 * 37, -10 * 64)
+            assert np.array_equal(b0, b1) and l1 == l0 + 37 and t1 == t0
+    nfont.close()
