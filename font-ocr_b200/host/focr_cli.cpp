@@ -304,6 +304,10 @@ int ncc_main(int argc, char **argv)
         fprintf(stderr, "ncc: --rust is not supported by the B200 path (DESIGN.md section 7)\n");
         return 2;
     }
+    if (a.on("--save-letters")) {   // diagnostics (ncc.rs:642-650): the Python front-end writes the template PNGs
+        fprintf(stderr, "ncc: --save-letters is only implemented by the Python front-end (python -m font_ocr_b200.cli ncc ...)\n");
+        return 2;
+    }
     if (a.on("--raw") && a.img.size() != 1) die("--raw takes exactly one image (ncc.rs:833-837)");
     const std::map<std::string, int> modes = {{"alphabet", 0}, {"font", 1}, {"char", 2}};
     if (!modes.count(a.s("--box-size"))) die("bad --box-size");   // the reference .unwrap()s the TryFrom error (ncc.rs:559)
