@@ -744,10 +744,10 @@ static int stage_threads()
         const unsigned hc = std::max(2u, std::thread::hardware_concurrency());
         int ranks = 1;
         if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
-        return (int)std::max(1u, std::min(8u, hc / (unsigned)ranks));
+        return (int)std::max(4u, std::min(8u, hc / (unsigned)ranks));   // (4 oversubscribed threads still beat 2: the copies wait on memory)
     }();
     if (base < 0) return -base;
-    return std::max(1, base / g_stage_sharers.load());
+    return std::max(std::min(base, 4), base / g_stage_sharers.load());
 }
 
 // rows x row_bytes from src (stride src_stride) to dst (stride dst_stride), split over the staging threads
