@@ -37,15 +37,18 @@
 //    sees zero-padded template rows, and the fp16 MMA's two 16-byte K chunks carry one set of window statistics each
 //    (a column's B2 entry is non-zero only in the chunk of its own box size).
 //  * A JOB = one output row x one sub-block of <= 256 columns (a launch has 1 or 2 sub-blocks per row).  Jobs walk a
-//    RING of TMEM accumulators (512 / columns per sub-block of them): ONE warp issues all jobs in order (converged, all
-//    its state in uniform registers), the tensor pipe executes them in order, two teams of 8 epilogue warps drain
-//    alternate jobs and hand the accumulator back before they screen their last chunks.  With three accumulators the
+//    RING of TMEM accumulators (512 / columns per sub-block of them): TWO converged warps issue alternate jobs (all
+//    their state in uniform registers), two teams of 4 epilogue warps (one per TMEM lane quarter) drain alternate jobs and
+//    hand the accumulator back as soon as their last tcgen05.ld has landed, before they screen.  With three accumulators the
 //    hand-back chain (commit -> team wakes -> tcgen05.ld -> release -> issuer wakes) has two whole jobs of tensor time.
+//  * Columns are ordered by template similarity (tc_class_build): a window that matches a glyph matches its look-alikes,
+//    and clustering them into the same 32-column unit makes the epilogue's slow path run once for them, not once per unit.
+//  * Boxes at most 8 wide pack two template rows per 16-byte K chunk (ring slot r = 8-byte windows of page rows r, r+1).
 //
 // Warp roles (one persistent CTA per SM over (page, x-strip, y-segment) items):
-//   warp 0     TMA producer of raw page rows         warp 1      MMA issuer (converged warp, elect.sync-guarded tcgen05)
+//   warp 0     TMA producer of raw page rows         warps 1-2   MMA issuers (converged warps, elect.sync-guarded tcgen05)
 //   warp 3     TMEM alloc, otherwise idle            warps 4-7   Toeplitz expansion (one warp per row)
-//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-27 epilogue (2 teams x 2 per TMEM lane quarter)
+//   warps 8-11 A2 rows (window statistics -> fp16)   warps 12-19 epilogue (2 teams x 4 TMEM lane quarters)
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
