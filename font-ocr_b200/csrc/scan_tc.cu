@@ -1165,18 +1165,19 @@ static std::vector<uint32_t> similarity_order(const TcClassSrc *src, uint32_t nc
     for (uint32_t i = 0; i < n_tpl; i++) pos[i] = i;
     if (n_tpl < 3 || n_tpl > 4096 || getenv("FOCR_TC_NOREORDER")) return pos;
     (void)ncls;
-    const size_t K = (size_t)n_h * np;
+    // (large banks of large boxes: every `stride`-th pixel is enough to tell look-alikes apart and bounds the n^2 * K work)
+    const size_t K0 = (size_t)n_h * np, stride = (n_tpl > 512 && K0 > 256) ? K0 / 256 : 1, K = (K0 + stride - 1) / stride;
     std::vector<float> vec((size_t)n_tpl * K);
     for (uint32_t i = 0; i < n_tpl; i++) {
         const uint32_t bs = i < n_tpl0 ? 0 : 1, li = bs ? i - n_tpl0 : i;
-        const uint8_t *t = src[bs].rows_host + (size_t)li * K;
+        const uint8_t *t = src[bs].rows_host + (size_t)li * K0;
         double mean = 0;
-        for (size_t k = 0; k < K; k++) mean += t[k];
+        for (size_t k = 0; k < K; k++) mean += t[k * stride];
         mean /= (double)K;
         double nrm = 0;
-        for (size_t k = 0; k < K; k++) nrm += (t[k] - mean) * (t[k] - mean);
+        for (size_t k = 0; k < K; k++) nrm += (t[k * stride] - mean) * (t[k * stride] - mean);
         const double inv = nrm > 0 ? 1.0 / std::sqrt(nrm) : 0.0;
-        for (size_t k = 0; k < K; k++) vec[(size_t)i * K + k] = (float)((t[k] - mean) * inv);
+        for (size_t k = 0; k < K; k++) vec[(size_t)i * K + k] = (float)((t[k * stride] - mean) * inv);
     }
     std::vector<float> sim((size_t)n_tpl * n_tpl);
     auto rows = [&](uint32_t i0, uint32_t step) {
