@@ -1053,18 +1053,12 @@ struct CandArgs {
     uint32_t cand_cap, n_lists;
     const unsigned int *cand_count;  // [n_lists]
     unsigned int *cand_max;  // high-water mark of a list's count (overflow detection on the host)
-    const uint32_t *tpl_of;  // [n_blocks*nb] bank index per group column (0xFFFFFFFF = padding)
-    const uint32_t *cls_of;  // [n_blocks*nb] index of the column's template within `rows`
-    const uint8_t *rows;     // [n_tpl][n_h][np] zero-padded template rows of the group
-    const TplInfo *tpl;
+    const TcColInfo *col_info;   // [n_blocks*nb] per group column: template constants, bank index (0xFFFFFFFF = padding), box size
+    const uint8_t *rows;         // [n_blocks*nb][n_h][np] zero-padded template rows in column order
     const uint8_t *inv;
     size_t inv_page_stride;
     int pitch, n_h, np;
     int n_w[2];              // box widths of the group (one or two box sizes of the same height)
-    const uint32_t *sp[2];   // window-sum planes per box size
-    int pack;                // ... holding packed words: s_p is the low half
-    int spitch;
-    size_t plane_page_stride;
     double n_d[2], thr_d;
     HitSink sink;
 };
@@ -1078,25 +1072,23 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
         const Hit *list = a.cands + (size_t)l * a.cand_cap;
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
             const Hit c = list[i];
-            const uint32_t t = a.tpl_of[c.t];
+            // everything the candidate needs hangs off its record directly (column -> constants and template rows, window ->
+            // page rows): ONE dependent round trip after the list read, then the rows stream
+            const TcColInfo ti = a.col_info[c.t];
+            const uint32_t t = ti.bank_t;
             if (t == 0xFFFFFFFFu) continue;
             const uint32_t y = c.yx >> 16, x = c.yx & 0xFFFFu;
             // exact numerator: u8 x u8 -> u32 with __dp4a on byte-shifted page words; the template rows are
             // zero padded to np bytes, so bytes beyond n_w contribute nothing
-            const uint32_t *trow = (const uint32_t *)(a.rows + (size_t)a.cls_of[c.t] * a.n_h * a.np);
+            const uint32_t *trow = (const uint32_t *)(a.rows + (size_t)c.t * a.n_h * a.np);
             const uint8_t *p0 = a.inv + (size_t)c.page * a.inv_page_stride + (size_t)y * a.pitch + x;
             const int sh = (int)((uintptr_t)p0 & 3) * 8, nw4 = a.np >> 2;
             const uint32_t *prow = (const uint32_t *)((uintptr_t)p0 & ~(uintptr_t)3);
-            // ... and the window's sum of squares (ncc.rs:308) from the same words, bytes beyond n_w masked off: the
-            // tcgen05 path does not materialise an s2p plane (4 B per window of HBM traffic saved in window_stats)
-            // (issued first: the statistics and the template record are random 4..32-byte reads whose latency then overlaps the rows)
-            const size_t o = (size_t)c.page * a.plane_page_stride + (size_t)y * a.spitch + x;
-            const TplInfo ti = a.tpl[t];
-            const int bs = (int)ti.n_w == a.n_w[0] ? 0 : 1;   // which box size of the group
-            const uint32_t s_pw = __ldg(a.sp[bs] + o);
-            const uint32_t s_p = a.pack ? (s_pw & 0xFFFFu) : s_pw;
+            // ... and the window's sum and sum of squares (ncc.rs:307-308) from the same words, bytes beyond n_w masked off:
+            // the exact pass reads no statistics plane
+            const int bs = (int)ti.bs;
             const int n_w = a.n_w[bs];
-            uint32_t acc = 0, s2_p = 0;
+            uint32_t acc = 0, s2_p = 0, s_p = 0;
             const int pitch4 = a.pitch >> 2;
             auto rows = [&](auto nw4_c) {   // nw4_c: words per template row as a compile-time constant (0: run-time nw4)
                 constexpr int NW4 = decltype(nw4_c)::value;
@@ -1117,6 +1109,7 @@ __global__ void __launch_bounds__(256) cand_exact_kernel(CandArgs a)
                             const int valid = n_w - 4 * q;   // bytes of this word inside the window
                             const uint32_t wm = valid >= 4 ? w : (valid <= 0 ? 0u : (w & ((1u << (8 * valid)) - 1u)));
                             s2_p = __dp4a(wm, wm, s2_p);
+                            s_p = __dp4a(wm, 0x01010101u, s_p);
                             lo = hi;
                         }
                     }
@@ -1296,8 +1289,8 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     const size_t subtile = (size_t)2 * tc.ksteps * tc.nbsub * 16, tile = subtile * tc.nsub;
     std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
     std::vector<float4> cst((size_t)tc.n_blocks * tc.nb);
-    std::vector<uint32_t> tof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu), cof((size_t)tc.n_blocks * tc.nb, 0xFFFFFFFFu);
-    std::vector<uint8_t> rows_all((size_t)n_tpl * n_h * np);
+    std::vector<uint8_t> rows_all((size_t)tc.n_blocks * tc.nb * n_h * np, 0);   // column order, zero for padding columns
+    std::vector<TcColInfo> cinfo((size_t)tc.n_blocks * tc.nb, TcColInfo{0., 0., 0., 0xFFFFFFFFu, 0u});
     const float inf = INFINITY;
     for (auto &c : cst) c = make_float4(inf, 0.f, 0.f, 0.f);
     for (int c = 0; c < 2; c++) {
@@ -1309,7 +1302,7 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     // matches a glyph matches its look-alikes too -- the same letter at the neighbouring subpixel shifts first of all, which
     // the bank order (offset index, letter) puts a whole alphabet apart.  Similar templates are therefore placed in
     // the same 32-column unit (clusters over the templates' normalised correlations), so that a matching window's survivors
-    // fall into one unit instead of several (config 3: correlation kernel 0.414 -> 0.383 ms/page).  Results are indexed through tpl_of / cls_of: the order of
+    // fall into one unit instead of several (config 3: correlation kernel 0.414 -> 0.383 ms/page).  Results are indexed through the per-column records (TcColInfo): the order of
     // the columns is invisible outside the kernel.
     std::vector<uint32_t> unit_caps;   // sizes of the epilogue's column units in column order
     for (uint32_t b = 0; b < tc.n_blocks; b++)
@@ -1319,7 +1312,6 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     for (uint32_t i = 0; i < n_tpl; i++) {
         const uint32_t bs = i < tc.n_tpl0 ? 0 : 1, li = bs ? i - tc.n_tpl0 : i;   // box size, index within it
         const uint8_t *trows = src[bs].rows_host + (size_t)li * n_h * np;
-        memcpy(&rows_all[(size_t)i * n_h * np], trows, (size_t)n_h * np);
         const uint32_t ip = pos[i];                                               // place in the column order
         const uint32_t blk = ip / per_blk, r = ip % per_blk, sub = r / per_sub, n = r % per_sub;
         const uint32_t col = sub * tc.nbsub + n;
@@ -1342,23 +1334,21 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
         const double norm_n = scale / ti.rnorm_n, b_t = scale * ti.s_n * ti.n_recip;
         const bool ok = std::isfinite(ti.rnorm_n) && ti.rnorm_n > 0 && std::isfinite(norm_n);
         cst[(size_t)blk * tc.nb + col] = make_float4(ok ? (float)norm_n : inf, (float)b_t, (float)bs, 0.f);
-        tof[(size_t)blk * tc.nb + col] = src[bs].bank_index[li];
-        cof[(size_t)blk * tc.nb + col] = i;
+        memcpy(&rows_all[((size_t)blk * tc.nb + col) * n_h * np], trows, (size_t)n_h * np);
+        cinfo[(size_t)blk * tc.nb + col] = TcColInfo{ti.rnorm_n, ti.n_recip, ti.s_n, src[bs].bank_index[li], bs};
         tc.col_of[i] = blk * tc.nb + col;
         if (ok) {
             tc.blk_bmax[bs][blk] = std::max(tc.blk_bmax[bs][blk], (float)b_t);
             tc.blk_normmax[bs][blk] = std::max(tc.blk_normmax[bs][blk], (float)norm_n);
         }
     }
-    if (cudaMalloc(&tc.cls_of, cof.size() * 4) != cudaSuccess) return -1;
-    if (cudaMemcpy(tc.cls_of, cof.data(), cof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.b_tiles, bt.size()) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.consts, cst.size() * sizeof(float4)) != cudaSuccess) return -1;
-    if (cudaMalloc(&tc.tpl_of, tof.size() * 4) != cudaSuccess) return -1;
     if (cudaMalloc(&tc.rows, rows_all.size()) != cudaSuccess) return -1;
+    if (cudaMalloc(&tc.col_info, cinfo.size() * sizeof(TcColInfo)) != cudaSuccess) return -1;
+    if (cudaMemcpy(tc.col_info, cinfo.data(), cinfo.size() * sizeof(TcColInfo), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.b_tiles, bt.data(), bt.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.consts, cst.data(), cst.size() * sizeof(float4), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
-    if (cudaMemcpy(tc.tpl_of, tof.data(), tof.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     if (cudaMemcpy(tc.rows, rows_all.data(), rows_all.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     tc.supported = true;
     return 0;
@@ -1368,13 +1358,11 @@ void tc_class_release(TcClass &tc)
 {
     if (tc.b_tiles) cudaFree(tc.b_tiles);
     if (tc.consts) cudaFree(tc.consts);
-    if (tc.tpl_of) cudaFree(tc.tpl_of);
-    if (tc.cls_of) cudaFree(tc.cls_of);
     if (tc.rows) cudaFree(tc.rows);
-    tc.cls_of = nullptr;
+    if (tc.col_info) cudaFree(tc.col_info);
+    tc.col_info = nullptr;
     tc.b_tiles = nullptr;
     tc.consts = nullptr;
-    tc.tpl_of = nullptr;
     tc.rows = nullptr;
     tc.supported = false;
 }
@@ -1549,10 +1537,8 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         ca.n_lists = (uint32_t)grid * TC_LISTS_PER_CTA;
         ca.cand_count = a.cand_count;
         ca.cand_max = a.cand_max;
-        ca.tpl_of = tc.tpl_of;
-        ca.cls_of = tc.cls_of;
+        ca.col_info = (const TcColInfo *)tc.col_info;
         ca.rows = tc.rows;
-        ca.tpl = a.tpl;
         ca.inv = a.inv;
         ca.inv_page_stride = a.inv_page_stride;
         ca.pitch = a.pitch;
@@ -1560,11 +1546,6 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
         ca.np = tc.np;
         ca.n_w[0] = tc.n_w;
         ca.n_w[1] = tc.ncls == 2 ? tc.n_w2 : tc.n_w;
-        ca.sp[0] = p.sp[0];
-        ca.sp[1] = p.sp[1];
-        ca.pack = p.pack;
-        ca.spitch = a.spitch;
-        ca.plane_page_stride = a.plane_page_stride;
         ca.n_d[0] = (double)(ca.n_w[0] * tc.n_h);
         ca.n_d[1] = (double)(ca.n_w[1] * tc.n_h);
         ca.thr_d = a.thr_d;

@@ -33,11 +33,17 @@ struct TcClass {
     uint32_t ksteps = 0;    // tcgen05.mma instructions per output tile = ceil(kchunks/2) (K = 32 each)
     uint8_t *b_tiles = nullptr;   // device [n_blocks][nsub][2*ksteps][nbsub][16]
     float4 *consts = nullptr;     // device [n_blocks*nb] {norm_n, s_n/n, box size index as float, -}; norm_n = +inf for padding / constant templates
-    uint32_t *tpl_of = nullptr;   // device [n_blocks*nb] bank index (0xFFFFFFFF for padding)
-    uint32_t *cls_of = nullptr;   // device [n_blocks*nb] index within the group's template rows (0xFFFFFFFF for padding)
-    uint8_t *rows = nullptr;      // device [n_tpl][n_h][np] zero-padded template rows of the group (exact pass)
+    uint8_t *rows = nullptr;      // device [n_blocks*nb][n_h][np] zero-padded template rows in COLUMN order (exact pass; zero for padding columns)
+    void *col_info = nullptr;     // device [n_blocks*nb] TcColInfo: what the exact pass needs per column, one 32-byte record
     std::vector<uint32_t> col_of; // host, per group-local template: its column (launch * nb + column)
     std::vector<float> blk_bmax[2], blk_normmax[2];  // host, per N-block and box size: max s_n/n and max norm_n over its real columns
+};
+
+// per column of a launch group: the template's constants for the exact pass (ncc.cpp:73-86), its bank index and box size
+struct __align__(16) TcColInfo {
+    double rnorm_n, n_recip, s_n;
+    uint32_t bank_t;   // 0xFFFFFFFF: padding column
+    uint32_t bs;       // which box size of the group (0 or 1)
 };
 
 // one box size going into a launch group
