@@ -1,2 +1,1 @@
-timeout 300 python tools/prof_run.py 16 0.8 2>&1 | grep "scan\|Error" | tail -2
-timeout 900 python -m pytest tests/test_gpu_ncc.py -x -q -m gpu 2>&1 | tail -4
+for sp in 1 2 4 8; do echo "split $sp"; FOCR_EXACT_SPLIT=$sp timeout 300 python tools/prof_run.py 16 0.8 2>&1 | grep "scan\|Error" | tail -1; done
