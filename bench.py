@@ -107,7 +107,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.proc, self.lines = device, None, []   # lines: (time received, text)
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -120,15 +121,28 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)   # the sampler's last line may still be in flight
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # only the samples taken between mark_begin() and mark_end(): the timed legs (nvidia-smi is started long before,
+        # it needs up to a second to deliver its first line)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else time.time()) + 0.06
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -492,6 +506,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         cpu_group = dist.new_group(backend="gloo")   # host-side waits that must not occupy the GPUs
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local)   # started now (nvidia-smi takes a while to deliver); only the timed legs' samples are used
+    sampler.start()
     from font_ocr_b200 import native, ncc
 
     pkg, font, bank_h = make_bank()
@@ -551,11 +567,15 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), ctx.launch_count - l0, prof
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    for _ in range(args.warmup):   # warm up before the clock samples are marked (timed() warms up again: cheap)
+        step_device()
+    ctx.sync()
+    sampler.mark_begin()
     ms_dev, launches, prof = timed(step_device, args.steps, args.warmup, profile=True)
-    clocks = sampler.stop()
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 1))
+    sampler.mark_end()
+    clocks = sampler.stop()
+    clocks["window"] = "the device-resident and end-to-end timed legs (warm-up steps of those legs included), nvidia-smi -lms 50"
     # the device-resident and the host-buffer paths must agree byte for byte (this also reads the results back)
     chk_counts = counts_dev.cpu().numpy().view(np.uint32).reshape(P, T)
     chk_m = out_dev.cpu().numpy().view(native.MATCH_DTYPE).reshape(P, T, N_OUT)
