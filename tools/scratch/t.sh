@@ -1,2 +1,1 @@
-timeout 600 python bench.py --no-cpu --no-small --no-focr --no-config5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['clocks'])"
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu --no-small --no-focr --no-config5 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value'], d['clocks'])"
+timeout 900 python bench.py > gpurun_out/r2_bench.log 2> gpurun_out/r2_bench.err; echo "bench rc=$?"
