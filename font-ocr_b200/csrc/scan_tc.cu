@@ -107,7 +107,8 @@ struct TcParams {
     int nb;            // columns per launch = nsub * nbs
     int nsub;          // sub-blocks: jobs (accumulators) per output row
     int nunits;        // 32-column epilogue units per accumulator
-    int nbs;           // columns per sub-block = N of the MMAs = TMEM column stride between accumulators (multiple of 32)
+    int nbs;           // columns per sub-block = TMEM column stride between accumulators = column stride of the B tile (multiple of 32)
+    int nmma[2];       // N of the MMAs per sub-block: its real columns rounded up to 16 (<= nbs; the columns beyond are never written)
     int nbuf;          // accumulators in the ring: job k uses number k mod nbuf
     int ring;          // expanded-row ring slots = ring_groups * 4
     int ring_groups;
@@ -329,6 +330,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+// zero 16 columns of this warp's lane quarter
+__device__ __forceinline__ void tc_st16_zero(uint32_t taddr)
+{
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t tc_ld1(uint32_t taddr)
 {
     uint32_t v;
@@ -453,14 +462,17 @@ template <bool LEAN, uint32_t MW>
 __device__ __forceinline__ void tc_mma_role(const TcParams &p, const TcSmem &sm, const uint32_t leader)
 {
     constexpr uint32_t mw = MW;
+    // N of this warp's MMAs: with two sub-blocks per row the jobs of parity mw ARE sub-block mw; the real columns of a
+    // sub-block rounded up to 16 (not to the 32 of the epilogue's units: an MMA takes N / 2 cycles)
+    const uint32_t nmma = (uint32_t)(p.nsub == 2 ? p.nmma[mw] : p.nmma[0]);
     const uint32_t idesc8 = (2u << 4)                          // D format: S32
                             | (0u << 7) | (0u << 10)           // A, B: unsigned 8-bit
                             | (0u << 15) | (0u << 16)          // A, B: K-major
-                            | ((uint32_t)(p.nbs >> 3) << 17)   // N
+                            | ((nmma >> 3) << 17)              // N
                             | ((128u >> 4) << 24);             // M = 128
     const uint32_t idesc16 = (1u << 4)                         // D format: F32 (same TMEM columns, read as fp32)
                              | (0u << 7) | (0u << 10)          // A, B: F16
-                             | ((uint32_t)(p.nbs >> 3) << 17) | ((128u >> 4) << 24);
+                             | ((nmma >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t ring_n = p.ring, ring_g = p.ring_groups, nbuf = p.nbuf, ksteps = p.ksteps, n_hp = p.n_hp, nbs = p.nbs,
                    nsub = p.nsub;
     const uint32_t b_lbo16 = (uint32_t)p.nbs, b_inc = 2 * b_lbo16;      // 16-byte units: K chunks of B are nbs columns apart
@@ -921,6 +933,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         uint32_t my_count = 0;
         float *const scratch = (float *)(epi_scratch + e * 128);   // one lane's 32 values at a time (candidate extraction)
         const unsigned lane_lt = (1u << lane) - 1u;
+        // columns of the accumulators that no MMA of this launch writes (N is rounded up to 16, the units to 32): zero them
+        // once, or whatever an earlier kernel left there would be screened row after row
+        {
+            const int n_min = min(p.nmma[0], p.nsub == 2 ? p.nmma[1] : p.nmma[0]);
+            for (uint32_t a = 0; a < p.nbuf; a++)
+                for (int c0 = n_min; c0 < p.nbs; c0 += 16) tc_st16_zero(tlane + a * p.nbs + c0);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         const bool no_ld = TC_EXP && (p.dbg_mode & 1), no_screen = TC_EXP && (p.dbg_mode & 2);
         const int dbg_sub = p.dbg_acc ? p.dbg_col / p.nbs : -1, dbg_c = p.dbg_acc ? p.dbg_col % p.nbs : 0;
         TT_BEGIN();
@@ -1285,9 +1305,17 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     tc.n_blocks = (n_tpl + nb_max - 1) / nb_max;
     const uint32_t per_blk = (n_tpl + tc.n_blocks - 1) / tc.n_blocks;   // templates per launch
     tc.nsub = (per_blk > 256 || (per_blk > 64 && getenv("FOCR_TC_SPLIT"))) ? 2 : 1;
-    const uint32_t per_sub = (per_blk + tc.nsub - 1) / tc.nsub;
-    tc.nbsub = (per_sub + 31) & ~31u;
+    tc.nbsub = ((per_blk + tc.nsub - 1) / tc.nsub + 31) & ~31u;
     tc.nb = tc.nsub * tc.nbsub;
+    // columns of a launch over its sub-blocks: the first one full (a whole number of 32-column units), the rest in the
+    // second -- whose MMAs then only span its real columns rounded up to 16 (296 columns: 160 + 136 -> N = 160 and 144)
+    auto cols0_of = [&](uint32_t cnt) { return std::min(cnt, tc.nbsub); };
+    for (int c = 0; c < 2; c++) tc.blk_nmma[c].assign(tc.n_blocks, 16);
+    for (uint32_t b = 0; b < tc.n_blocks; b++) {
+        const uint32_t cnt = std::min(per_blk, n_tpl - b * per_blk), c0 = cols0_of(cnt), c1 = cnt - c0;
+        tc.blk_nmma[0][b] = std::max(16u, (c0 + 15) & ~15u);
+        tc.blk_nmma[1][b] = std::max(16u, (c1 + 15) & ~15u);
+    }
     const size_t subtile = (size_t)2 * tc.ksteps * tc.nbsub * 16, tile = subtile * tc.nsub;
     std::vector<uint8_t> bt(tile * tc.n_blocks, 0);
     std::vector<float4> cst((size_t)tc.n_blocks * tc.nb);
@@ -1309,13 +1337,17 @@ int tc_class_build(TcClass &tc, const TcClassSrc *src, uint32_t ncls, uint32_t n
     std::vector<uint32_t> unit_caps;   // sizes of the epilogue's column units in column order
     for (uint32_t b = 0; b < tc.n_blocks; b++)
         for (uint32_t sb = 0; sb < tc.nsub; sb++)
-            for (uint32_t c0 = 0; c0 < per_sub; c0 += 32) unit_caps.push_back(std::min(32u, per_sub - c0));
+        {
+            const uint32_t cnt = std::min(per_blk, n_tpl - b * per_blk), in_sub = sb == 0 ? cols0_of(cnt) : cnt - cols0_of(cnt);
+            for (uint32_t c0 = 0; c0 < in_sub; c0 += 32) unit_caps.push_back(std::min(32u, in_sub - c0));
+        }
     const std::vector<uint32_t> pos = similarity_order(src, ncls, tc.n_tpl0, n_tpl, n_h, np, unit_caps);
     for (uint32_t i = 0; i < n_tpl; i++) {
         const uint32_t bs = i < tc.n_tpl0 ? 0 : 1, li = bs ? i - tc.n_tpl0 : i;   // box size, index within it
         const uint8_t *trows = src[bs].rows_host + (size_t)li * n_h * np;
         const uint32_t ip = pos[i];                                               // place in the column order
-        const uint32_t blk = ip / per_blk, r = ip % per_blk, sub = r / per_sub, n = r % per_sub;
+        const uint32_t blk = ip / per_blk, r = ip % per_blk;
+        const uint32_t cols0 = cols0_of(std::min(per_blk, n_tpl - blk * per_blk)), sub = r < cols0 ? 0 : 1, n = r - sub * cols0;
         const uint32_t col = sub * tc.nbsub + n;
         for (uint32_t kc = 0; kc < tc.kchunks; kc++) {
             uint8_t *dst = &bt[blk * tile + sub * subtile + ((size_t)kc * tc.nbsub + n) * 16];
@@ -1395,6 +1427,7 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     p.nsub = tc.nsub;
     p.nbs = tc.nbsub;
     p.nunits = tc.nbsub / 32;
+    p.nmma[0] = p.nmma[1] = tc.nbsub;   // (set per launch below)
     p.nbuf = std::min(512 / p.nbs, TC_MAX_BUF);
     if (const char *e = getenv("FOCR_TC_NBUF")) p.nbuf = std::max(1, std::min(p.nbuf, atoi(e)));   // experiments
     p.ring_groups = tc.ring_groups;   // rows y..y+n_hp-1 may straddle one more group; + look-ahead
@@ -1481,6 +1514,9 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
             p.timeline = tl != nullptr;
             p.tl0 = tl ? (uint32_t)atoi(tl) : 0;
         }
+        p.nmma[0] = (int)tc.blk_nmma[0][blk];
+        p.nmma[1] = (int)tc.blk_nmma[1][blk];
+        if (getenv("FOCR_TC_FULLN")) p.nmma[0] = p.nmma[1] = p.nbs;   // experiments: MMAs over the whole accumulator stride
         p.btile = tc.b_tiles + (size_t)blk * p.btile_bytes;
         p.colconst = tc.consts + (size_t)blk * tc.nb;
         p.col_base = blk * tc.nb;

@@ -36,6 +36,7 @@ struct TcClass {
     uint8_t *rows = nullptr;      // device [n_blocks*nb][n_h][np] zero-padded template rows in COLUMN order (exact pass; zero for padding columns)
     void *col_info = nullptr;     // device [n_blocks*nb] TcColInfo: what the exact pass needs per column, one 32-byte record
     std::vector<uint32_t> col_of; // host, per group-local template: its column (launch * nb + column)
+    std::vector<uint32_t> blk_nmma[2];   // host, per N-block and sub-block: N of the MMAs (real columns rounded up to 16)
     std::vector<float> blk_bmax[2], blk_normmax[2];  // host, per N-block and box size: max s_n/n and max norm_n over its real columns
 };
 
