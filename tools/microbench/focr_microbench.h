@@ -17,6 +17,8 @@ const char *focr_microbench_last_error(void);
  * accumulators; cycles_per_mma is the median over SMs, ms_total the CUDA-event time of the timed launch.
  * bench.py turns it into the measured int8 dense peak (MEASURED_PEAKS.json has no integer tensor peak). */
 int focr_bench_umma_i8(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma, double *ms_total);
+/* the same stream as cta_group::2 MMAs (M = 256) issued by the leader of every CTA pair */
+int focr_bench_umma_i8_2cta(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma, double *ms_total);
 double focr_bench_umma_issue_cycles(void);
 
 /* cycles per hand-shake round trip "signal (tcgen05.commit or arrive) -> nwait warps wait and answer -> the signaller

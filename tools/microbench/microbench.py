@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libfocr_microbench.so")
 SRC = os.path.join(HERE, "umma_bench.cu")
-SYMBOLS = ["focr_microbench_last_error", "focr_bench_umma_i8", "focr_bench_umma_issue_cycles", "focr_bench_pingpong",
+SYMBOLS = ["focr_microbench_last_error", "focr_bench_umma_i8", "focr_bench_umma_i8_2cta", "focr_bench_umma_issue_cycles", "focr_bench_pingpong",
            "focr_bench_tmem"]
 
 
@@ -41,6 +41,7 @@ def lib():
         vp, i = C.c_void_p, C.c_int
         l.focr_microbench_last_error.restype = C.c_char_p
         l.focr_bench_umma_i8.argtypes = [i, i, i, i, i, vp, vp]
+        l.focr_bench_umma_i8_2cta.argtypes = [i, i, i, i, i, vp, vp]
         l.focr_bench_umma_issue_cycles.restype = C.c_double
         l.focr_bench_pingpong.argtypes = [i, i, i, i, i, vp]
         l.focr_bench_tmem.argtypes = [i, i, i, i, i, i, vp, vp]

@@ -28,8 +28,12 @@ namespace focr {
 
 __device__ __forceinline__ uint32_t ub_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// PAIR: launched as clusters of two CTAs; the leader issues cta_group::2 MMAs (M = 256, each CTA holds N/2 columns of B)
+template <bool PAIR>
 __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps, int iters, int nacc, long long *cycles)
 {
+    uint32_t rank = 0;
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_ptr;
@@ -41,16 +45,22 @@ __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ub_smem_u32(&tmem_ptr)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ub_smem_u32(&tmem_ptr)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ub_smem_u32(&tmem_ptr)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_ptr;
     if (warp == 1) {
-        const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
         const uint32_t desc_hi = (128u >> 4) | (1u << 14);
         const uint32_t a0 = ((ub_smem_u32(smem) & 0x3FFFFu) >> 4) | ((2048u >> 4) << 16);
         const uint32_t bbase = ub_smem_u32(smem) + ksteps * 2 * 2048;
@@ -61,21 +71,32 @@ __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
         __syncwarp();
         t0 = clock64();
-        if (elected) {
+        if (elected && rank == 0) {
             for (int it = 0; it < iters; it++) {
                 const uint32_t d = tmem_base + (uint32_t)((it % nacc) * nbs);
                 for (int k = 0; k < ksteps; k++) {
                     const uint64_t ad = ((uint64_t)desc_hi << 32) | (a0 + (uint32_t)k * 2 * (2048 >> 4));
                     const uint64_t bd = ((uint64_t)desc_hi << 32) | (b0 + (uint32_t)k * 2 * ((uint32_t)n * 16u >> 4));
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
-                        "l"(ad), "l"(bd), "r"(idesc), "r"(k)
-                        : "memory");
+                    if (PAIR)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                            "l"(ad), "l"(bd), "r"(idesc), "r"(k)
+                            : "memory");
+                    else
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                            "l"(ad), "l"(bd), "r"(idesc), "r"(k)
+                            : "memory");
                 }
             }
             const long long ti = clock64();
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ub_smem_u32(&bar)) : "memory");
+            if (PAIR)
+                asm volatile("{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+                             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(ub_smem_u32(&bar)) : "memory");
+            else
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ub_smem_u32(&bar)) : "memory");
             cycles[gridDim.x + blockIdx.x] = ti - t0;  // when the issuing thread got past the last tcgen05.mma
         }
         __syncwarp();
@@ -88,10 +109,12 @@ __global__ void __launch_bounds__(128, 1) umma_i8_bench_kernel(int n, int ksteps
         if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (PAIR) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -280,8 +303,19 @@ static double g_last_issue_cycles = 0;
 extern "C" double focr_bench_umma_issue_cycles(void) { return g_last_issue_cycles; }
 
 // n: MMA N (multiple of 16, <= 256); returns the median over SMs of cycles per tcgen05.mma and the wall time
+static int umma_i8_impl(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma, double *ms_total, bool pair);
 extern "C" int focr_bench_umma_i8(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
                                   double *ms_total)
+{
+    return umma_i8_impl(device, n, ksteps, iters, nacc, cycles_per_mma, ms_total, false);
+}
+// the same stream issued as cta_group::2 MMAs (M = 256) by the leader of every CTA pair; cycles per MMA on the leader
+extern "C" int focr_bench_umma_i8_2cta(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma,
+                                       double *ms_total)
+{
+    return umma_i8_impl(device, n, ksteps, iters, nacc, cycles_per_mma, ms_total, true);
+}
+static int umma_i8_impl(int device, int n, int ksteps, int iters, int nacc, double *cycles_per_mma, double *ms_total, bool pair)
 {
     using namespace focr;
     if (device < 0 || !cycles_per_mma || !ms_total || n < 16 || n > 256 || (n & 15) || ksteps < 1 || ksteps > 16 || iters < 1 ||
@@ -294,13 +328,30 @@ extern "C" int focr_bench_umma_i8(int device, int n, int ksteps, int iters, int 
     long long *d = nullptr;
     if (cudaMalloc((void **)&d, sms * 16) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaMalloc");
     const size_t smem = (size_t)ksteps * 2 * (128 + n) * 16 + 1024;
-    if (cudaFuncSetAttribute(umma_i8_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaFuncSetAttribute");
+    void (*kernel)(int, int, int, int, long long *) = pair ? umma_i8_bench_kernel<true> : umma_i8_bench_kernel<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, "cudaFuncSetAttribute");
+    if (pair) sms &= ~1;
+    auto launch = [&](int its) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(sms);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pair ? 2 : 1;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, n, ksteps, its, nacc, d);
+    };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    umma_i8_bench_kernel<<<sms, 128, smem, st>>>(n, ksteps, 8, nacc, d);  // warm-up
+    launch(8);  // warm-up
     cudaEventRecord(e0, st);
-    umma_i8_bench_kernel<<<sms, 128, smem, st>>>(n, ksteps, iters, nacc, d);
+    launch(iters);
     cudaEventRecord(e1, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return focr_internal_fail(FOCR_ERR_CUDA, std::string("umma bench: ") + cudaGetErrorString(e));
