@@ -895,6 +895,36 @@ static int scan_host_impl(focr_ctx *c, const focr_bank *b, const uint8_t *pages_
     return fail(FOCR_ERR_NOMEM, "hit list kept overflowing");
 }
 
+// ---- page-locking for callers that have no CUDA binding of their own (include/focr_b200.h)
+extern "C" int focr_pin_register(focr_ctx *c, void *ptr, size_t bytes)
+{
+    if (!c || !ptr || bytes == 0) return fail(FOCR_ERR_ARG, "focr_pin_register: NULL argument or no bytes");
+    CU(cudaSetDevice(c->device));
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return FOCR_OK;
+}
+extern "C" int focr_pin_unregister(focr_ctx *c, void *ptr)
+{
+    if (!c || !ptr) return fail(FOCR_ERR_ARG, "focr_pin_unregister: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaHostUnregister(ptr));
+    return FOCR_OK;
+}
+extern "C" int focr_pin_alloc(focr_ctx *c, size_t bytes, void **out)
+{
+    if (!c || !out || bytes == 0) return fail(FOCR_ERR_ARG, "focr_pin_alloc: NULL argument or no bytes");
+    CU(cudaSetDevice(c->device));
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return FOCR_OK;
+}
+extern "C" int focr_pin_free(focr_ctx *c, void *ptr)
+{
+    if (!c || !ptr) return fail(FOCR_ERR_ARG, "focr_pin_free: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaFreeHost(ptr));
+    return FOCR_OK;
+}
+
 extern "C" int focr_ncc_scan(focr_ctx *c, const focr_bank *b, const uint8_t *pages_host, size_t page_stride,
                              uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
                              focr_match *out_host, uint32_t *counts_host)

@@ -23,6 +23,7 @@ SYMBOLS = [
     "focr_version", "focr_last_error", "focr_get_limits",
     "focr_ctx_create", "focr_ctx_destroy", "focr_ctx_set_kernel", "focr_ctx_stream", "focr_ctx_sync",
     "focr_ctx_launch_count", "focr_ctx_profile", "focr_ctx_profile_read",
+    "focr_pin_register", "focr_pin_unregister", "focr_pin_alloc", "focr_pin_free",
     "focr_bank_create", "focr_bank_destroy", "focr_bank_size",
     "focr_multi_create", "focr_multi_destroy", "focr_multi_size", "focr_multi_ctx", "focr_multi_page_block",
     "focr_multi_bank_create", "focr_multi_bank_destroy", "focr_multi_ncc_scan",
@@ -71,6 +72,10 @@ def lib():
     l.focr_ctx_launch_count.restype = u64
     l.focr_ctx_profile.argtypes = [vp, C.c_int]
     l.focr_ctx_profile_read.argtypes = [vp, vp, vp]
+    l.focr_pin_register.argtypes = [vp, vp, sz]
+    l.focr_pin_unregister.argtypes = [vp, vp]
+    l.focr_pin_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    l.focr_pin_free.argtypes = [vp, vp]
     l.focr_bank_create.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(vp)]
     l.focr_bank_destroy.argtypes = [vp]
     l.focr_bank_destroy.restype = None

@@ -16,6 +16,28 @@ from .native import MATCH_DTYPE, check, lib, ptr
 MAX_MATCHES = 1024  # ncc.rs:31
 
 
+class Pinned:
+    """A numpy array page-locked through the library (include/focr_b200.h: focr_pin_register)."""
+
+    def __init__(self, ctx: "Context", a: np.ndarray):
+        if not a.flags.c_contiguous:
+            raise ValueError("pin: the array must be C-contiguous")
+        self.ctx, self.array = ctx, a
+        check(lib().focr_pin_register(ctx._h, ptr(a), a.nbytes))
+        self._live = True
+
+    def release(self):
+        if self._live:
+            self._live = False
+            check(lib().focr_pin_unregister(self.ctx._h, ptr(self.array)))
+
+    def __enter__(self):
+        return self.array
+
+    def __exit__(self, *exc):
+        self.release()
+
+
 class Context:
     """focr_ctx: one per GPU."""
 
@@ -49,6 +71,11 @@ class Context:
         n = np.zeros(6, np.uint64)
         check(lib().focr_ctx_profile_read(self._h, ptr(ms), ptr(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("invert", "stats", "scan", "finalize", "exact", "decode"))}
+
+    def pin(self, a: np.ndarray) -> "Pinned":
+        """Page-lock a caller-owned array in place (focr_pin_register): scans then DMA from / into it directly instead
+        of staging it.  Use as a context manager, or call .release() when the array is no longer scanned."""
+        return Pinned(self, a)
 
     def close(self):
         if self._h:

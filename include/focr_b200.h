@@ -133,6 +133,16 @@ int focr_ncc_scan(focr_ctx *ctx, const focr_bank *bank, const uint8_t *pages_hos
                   uint32_t r_w, uint32_t r_h, uint32_t n_pages, float threshold, uint32_t n_out,
                   focr_match *out_host, uint32_t *counts_host);
 
+/* Page-locking for callers without a CUDA binding of their own (the Rust side of INTEGRATION.md): pin a buffer the
+ * caller already owns -- the Vec<u8> of pages (ncc.rs:575), the match / count arrays -- so that focr_ncc_scan and
+ * focr_decode_pages DMA from / into it directly instead of staging it (config 3: 2070 instead of ~1750 pages/s), or
+ * allocate pinned memory outright.  Registration costs ~0.1 ms per MB once; keep it for the lifetime of the buffer.
+ * focr_pin_unregister / focr_pin_free must see the same pointer.  Pinned memory is valid for every context. */
+int focr_pin_register(focr_ctx *ctx, void *ptr, size_t bytes);
+int focr_pin_unregister(focr_ctx *ctx, void *ptr);
+int focr_pin_alloc(focr_ctx *ctx, size_t bytes, void **out);
+int focr_pin_free(focr_ctx *ctx, void *ptr);
+
 /* Same scan with the pages already resident in device memory (gray, row pitch `pitch` bytes) and
  * the results left in device memory.  All work is enqueued on focr_ctx_stream() back to back; the
  * call then waits ONCE for the stream and checks the chunks' overflow flags (a candidate or hit list

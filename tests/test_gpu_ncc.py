@@ -403,6 +403,53 @@ def test_host_scan_slot_reuse_overflow_and_staging(built_lib, oracle):
         c.close()
 
 
+def test_host_register_pins_caller_buffers(built_lib):
+    """focr_pin_register / focr_pin_alloc (the page-locking a Rust caller has no CUDA binding for): a registered numpy
+    buffer is seen as pinned by the staging decision, scans of registered buffers are byte-identical to staged ones, and
+    unregistering restores the pageable path."""
+    import ctypes as C
+    from font_ocr_b200 import native, ncc
+
+    rng = np.random.default_rng(5)
+    P, H, W, n_out = 6, 120, 200, 32
+    pages = _noise_batch(rng, P, H, W)
+    tpls = [rng.integers(0, 256, (9, 9), dtype=np.uint8) for _ in range(12)]
+    c = ncc.Context(0)
+    try:
+        lib = native.lib()
+        is_pinned = getattr(lib, "_Z25focr_internal_host_pinnedPKv")   # the staging decision's own test (C++ linkage, internal)
+        is_pinned.argtypes, is_pinned.restype = [C.c_void_p], C.c_bool
+        bank = ncc.Bank(c, tpls)
+        m0, c0 = ncc.scan_pages(c, bank, pages, 0.3, n_out)                     # pageable: staged
+        out = np.zeros((P, len(tpls), n_out), native.MATCH_DTYPE)
+        cnt = np.zeros((P, len(tpls)), np.uint32)
+        assert not is_pinned(native.ptr(pages))
+        with c.pin(pages), c.pin(out), c.pin(cnt):
+            assert is_pinned(native.ptr(pages)) and is_pinned(native.ptr(out))
+            ncc.scan_pages(c, bank, pages, 0.3, n_out, out=out, counts=cnt)       # direct DMA
+        assert not is_pinned(native.ptr(pages))
+        assert np.array_equal(cnt, c0)
+        for p in range(P):
+            for t in range(len(tpls)):
+                n = int(c0[p, t])
+                assert out[p, t, :n].tobytes() == m0[p, t, :n].tobytes(), (p, t)
+        # pinned memory straight from the library
+        buf = C.c_void_p()
+        native.check(lib.focr_pin_alloc(c._h, pages.nbytes, C.byref(buf)))
+        assert is_pinned(buf)
+        C.memmove(buf, native.ptr(pages), pages.nbytes)
+        view = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint8)), shape=(pages.nbytes,)).reshape(pages.shape)
+        m1, c1 = ncc.scan_pages(c, bank, view, 0.3, n_out)
+        assert np.array_equal(c1, c0) and all(m1[p, t, :int(c0[p, t])].tobytes() == m0[p, t, :int(c0[p, t])].tobytes()
+                                              for p in range(P) for t in range(len(tpls)))
+        del view
+        native.check(lib.focr_pin_free(c._h, buf))
+        assert lib.focr_pin_register(c._h, None, 16) != 0 and lib.focr_pin_unregister(c._h, native.ptr(pages)) != 0
+        bank.close()
+    finally:
+        c.close()
+
+
 def test_multi_device_scan_identical_to_single(ctx, oracle):
     """focr_multi_ncc_scan shards ONE batch by page over the contexts of a focr_multi (every visible GPU; on a one-GPU box two
     contexts on device 0, which exercises the same host threads, page blocks and gather) and must return exactly what the
