@@ -26,6 +26,9 @@ static thread_local std::string g_err;
 static int fail(int code, const std::string &msg)
 {
     g_err = msg;
+    // a CUDA error that is reported here must not surface again in the cudaGetLastError() check of the next launch
+    // (the runtime keeps a non-sticky error as "last error" until somebody reads it)
+    if (code == FOCR_ERR_CUDA) cudaGetLastError();
     return code;
 }
 // shared with focr_decode.cu
