@@ -445,6 +445,10 @@ def test_host_register_pins_caller_buffers(built_lib):
         del view
         native.check(lib.focr_pin_free(c._h, buf))
         assert lib.focr_pin_register(c._h, None, 16) != 0 and lib.focr_pin_unregister(c._h, native.ptr(pages)) != 0
+        assert b"unregister" in lib.focr_last_error().lower() or b"registered" in lib.focr_last_error().lower()
+        # a reported CUDA error must not resurface in the next call's launch checks
+        m2, c2 = ncc.scan_pages(c, bank, pages, 0.3, n_out)
+        assert np.array_equal(c2, c0)
         bank.close()
     finally:
         c.close()
