@@ -114,7 +114,7 @@ constexpr int FLAG_WORDS = 16;    // one 64-byte flag block per chunk
 constexpr int FLAG_BLOCKS = 64;   // chunks the device-resident scan may enqueue between two host checks
 
 struct Slot {  // everything one in-flight chunk of pages needs
-    DevBuf gray, inv, sp, s2p, pf, rn, sp2, pf2, rowcount, hits, cands, candcnt, sel, ycut, selcount, flags, out, counts, acc;
+    DevBuf gray, inv, sp, s2p, pf, rn, sp2, pf2, rowcount, hits, cands, candcnt, sel, ycut, flags, out, counts, acc;
     PinBuf gray_pin, out_pin, counts_pin;   // staging for callers whose host buffers are pageable (ncc.rs:575: a Rust Vec<u8>)
     unsigned int *flags_host = nullptr;  // pinned, FLAG_BLOCKS blocks of: [0] hit_count, [1] overflow, [2] cand_count,
                                          // [3] cand high-water mark, [4..9] scan_tc watchdog (raised, tag, info, CTA, warp, parity)
@@ -234,7 +234,7 @@ extern "C" void focr_ctx_destroy(focr_ctx *c)
     cudaDeviceSynchronize();
     for (auto &s : c->slot) {
         for (DevBuf *b : {&s.gray, &s.inv, &s.sp, &s.s2p, &s.pf, &s.rn, &s.sp2, &s.pf2, &s.rowcount, &s.hits, &s.cands, &s.candcnt, &s.sel, &s.ycut,
-                          &s.selcount, &s.flags, &s.out, &s.counts, &s.acc})
+                          &s.flags, &s.out, &s.counts, &s.acc})
             b->release();
         for (PinBuf *b : {&s.gray_pin, &s.out_pin, &s.counts_pin}) b->release();
         if (s.flags_host) cudaFreeHost(s.flags_host);
@@ -490,7 +490,9 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         CU(s.rn.ensure(g.plane_page_stride * nR * 8));
     }
     if (any_tc && any_pair) CU(s.sp2.ensure(g.plane_page_stride * nR * 4));   // paired groups are always packed (<= 256 pixels)
-    CU(s.rowcount.ensure(PTR * g.r_h * 4));
+    // per-row hit counts and, right behind them, the selection counters: ONE memset clears both
+    const size_t rowcount_bytes = (PT * g.r_h * 4 + 7) & ~(size_t)7;
+    CU(s.rowcount.ensure(((PTR * g.r_h * 4 + 7) & ~(size_t)7) + PTR * 8));
     CU(s.hits.ensure((size_t)s.hits_per_page * nR * sizeof(Hit)));
     const size_t n_lists = (size_t)c->sm_count * TC_LISTS_PER_CTA;
     if (any_tc) {
@@ -499,7 +501,6 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     }
     CU(s.sel.ensure(PTR * g.sel_cap * 8));
     CU(s.ycut.ensure(PTR * 4));
-    CU(s.selcount.ensure(PTR * 8));
     CU(s.flags.ensure(FLAG_BLOCKS * FLAG_WORDS * 4));
     unsigned int *const flags = s.flags.as<unsigned int>() + (size_t)flag_block * FLAG_WORDS;
 
@@ -509,8 +510,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
                                g.r_w, g.r_h, nB, invert, st));
     }
     c->launches++;
-    CU(cudaMemsetAsync(s.rowcount.p, 0, PT * g.r_h * 4, st));
-    CU(cudaMemsetAsync(s.selcount.p, 0, PT * 8, st));
+    CU(cudaMemsetAsync(s.rowcount.p, 0, rowcount_bytes + PT * 8, st));
     CU(cudaMemsetAsync(flags, 0, FLAG_WORDS * 4, st));
 
     HitSink sink;
@@ -582,7 +582,8 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
         a.cand_count = s.candcnt.as<unsigned int>();
         a.cand_max = flags + 3;
         a.acc_out = nullptr;
-        if (tc) CU(cudaMemsetAsync(a.cand_count, 0, n_lists * 4, st));
+        // (no clearing of cand_count: every epilogue warp of the launch writes its list's count when it is through, and the
+        // exact pass reads exactly the launch's lists)
         int nl = 0;
         {
             StageTimer tm(c, FOCR_STAGE_SCAN);
@@ -619,7 +620,7 @@ static int enqueue_chunk(focr_ctx *c, const focr_bank *b, Slot &s, const Geometr
     f.hit_cap = sink.hit_cap;
     f.rowcount = s.rowcount.as<unsigned int>();
     f.y_cut = s.ycut.as<uint32_t>();
-    f.sel_count = s.selcount.as<unsigned int>();
+    f.sel_count = (unsigned int *)(s.rowcount.as<uint8_t>() + rowcount_bytes);
     f.sel = s.sel.as<unsigned long long>();
     f.sel_cap = g.sel_cap;
     f.overflow = flags + 1;
