@@ -435,8 +435,9 @@ struct Geometry {
 
 static int make_geometry(uint32_t r_w, uint32_t r_h, uint32_t n_out, Geometry &g)
 {
-    if (r_w == 0 || r_h == 0 || r_w > 65535 || r_h > 65535 - PAGE_PAD_ROWS)
-        return fail(FOCR_ERR_ARG, "page dimensions must fit u16 (height <= 65533)");
+    if (r_w == 0 || r_h == 0) return fail(FOCR_ERR_ARG, "empty page");
+    if (r_w > 65535 || r_h > 65535 - PAGE_PAD_ROWS)   // u16 match coordinates (ncc.cpp:8); the staging kernel's grid.y
+        return fail(FOCR_ERR_UNSUPPORTED, "page larger than focr_get_limits() allows (height <= " + std::to_string(65535 - PAGE_PAD_ROWS) + ")");
     if (n_out == 0 || n_out > 4096) return fail(FOCR_ERR_ARG, "n_out must be in 1..4096");
     g.r_w = r_w;
     g.r_h = r_h;

@@ -308,6 +308,35 @@ def test_scan_edge_cases_vs_oracle(kctx, oracle):
     assert c.sum() == 0
 
 
+def test_maximum_page_sizes(kctx, oracle):
+    """The largest pages focr_get_limits advertises, against the oracle: the tallest page (u16 y coordinates, the grid.y limit of
+    the staging kernel) and the widest one (finalize's shared-memory sort holds a whole row of keys); one pixel more is
+    refused with FOCR_ERR_UNSUPPORTED instead of a CUDA error."""
+    import ctypes as C
+    from font_ocr_b200 import native, ncc
+
+    lim = (C.c_uint32 * 5)()
+    native.lib().focr_get_limits(lim)
+    max_w, max_h = int(lim[2]), int(lim[3])
+    assert max_w >= 4096 and max_h >= 32768
+    rng = np.random.default_rng(31)
+    tpls = [rng.integers(0, 256, (9, 9), dtype=np.uint8) for _ in range(6)] + [rng.integers(0, 256, (14, 15), dtype=np.uint8) for _ in range(3)]
+    for shape in ((max_h, 48), (40, max_w)):
+        page = rng.integers(0, 256, shape, dtype=np.uint8)
+        page[rng.random(shape) < 0.6] = 255
+        for t in tpls[:3]:   # plant each template near the far corner so that the last rows / columns hold hits
+            h, w = t.shape
+            page[shape[0] - h - 1:shape[0] - 1, shape[1] - w - 2:shape[1] - 2] = 255 - t   # (the library scans 255 - p)
+        m, c = _scan(kctx, tpls, page, 0.3, 64)
+        s = oracle.Searcher(page, "port")
+        _assert_same(m[0], c[0], [s.search_c_u8(t, 0.3, n_out=64) for t in tpls], f"page {shape}")
+        assert c[0].sum() > 0
+    m, c = _scan(kctx, tpls[:3], rng.integers(0, 256, (max_h, 48), dtype=np.uint8), 0.999, 4)   # far-corner hit only
+    for shape in ((max_h + 1, 48), (40, max_w + 1)):
+        with pytest.raises(Unsupported):
+            _scan(kctx, tpls[:2], np.zeros(shape, np.uint8), 0.5, 1024)   # (the width limit is quoted for the reference's n_out)
+
+
 def test_sub_block_launch_matches_oracle(ctx, oracle, monkeypatch):
     """FOCR_TC_SPLIT=1: a launch covers its columns as two accumulator-sized sub-blocks per row (two jobs per row that
     share the row's operands).  Same results as the oracle."""
