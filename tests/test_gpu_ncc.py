@@ -206,6 +206,52 @@ def test_full_size_page_properties_and_sample(kctx, oracle, font, pkg):
         _assert_same(m[0, t:t + 1], c[0, t:t + 1], [exp], f"template {t}")
 
 
+def test_full_size_invariances(ctx, font, pkg):
+    """Properties at BASELINE config 3's full size that need no oracle: a page's match lists do not depend on the batch it
+    is scanned in (alone, in a batch through the chunked host pipeline, in another position through the device-resident entry),
+    a permuted bank permutes the lists (the tcgen05 path orders its columns by template similarity -- the bank order must not
+    leak), and the hits at a higher threshold are exactly the higher-scoring hits of the lower one (a prefix of them where the lower list was cut at n_out)."""
+    import torch
+    from font_ocr_b200 import native, ncc
+
+    tb = pkg.raster.TemplateBank(font, 13, x_bits=2)
+    tpls = [t.pixels for t in tb.templates]
+    T, n_out = len(tpls), 4096
+    pages = np.stack([pkg.pages.make_ncc_page(tb, 2480, 3508, seed=40 + i, shifts="bank")[0] for i in range(5)])
+    bank = ncc.Bank(ctx, tpls)
+    m_all, c_all = ncc.scan_pages(ctx, bank, pages, 0.8, n_out)                 # chunks of 2 + 3 pages
+    for p in (0, 3, 4):
+        m1, c1 = ncc.scan_pages(ctx, bank, pages[p], 0.8, n_out)
+        assert np.array_equal(c1[0], c_all[p]) and all(m1[0, t, :c1[0, t]].tobytes() == m_all[p, t, :c1[0, t]].tobytes() for t in range(T)), p
+    rev = torch.from_numpy(pages[::-1].copy()).cuda()
+    out_dev = torch.zeros(5 * T * n_out * 8, dtype=torch.uint8, device="cuda")
+    cnt_dev = torch.zeros(5 * T, dtype=torch.int32, device="cuda")
+    ncc.scan_pages_device(ctx, bank, rev.data_ptr(), 2480 * 3508, 2480, 2480, 3508, 5, 0.8, n_out, out_dev.data_ptr(), cnt_dev.data_ptr())
+    m_rev = out_dev.cpu().numpy().view(native.MATCH_DTYPE).reshape(5, T, n_out)
+    c_rev = cnt_dev.cpu().numpy().view(np.uint32).reshape(5, T)
+    for p in range(5):
+        assert np.array_equal(c_rev[4 - p], c_all[p])
+        assert all(m_rev[4 - p, t, :c_all[p, t]].tobytes() == m_all[p, t, :c_all[p, t]].tobytes() for t in range(T)), p
+    bank.close()
+    # a permuted bank
+    perm = np.random.default_rng(4).permutation(T)
+    bank_p = ncc.Bank(ctx, [tpls[i] for i in perm])
+    m_p, c_p = ncc.scan_pages(ctx, bank_p, pages[1], 0.8, n_out)
+    for k, t in enumerate(perm):
+        assert c_p[0, k] == c_all[1, t] and m_p[0, k, :c_p[0, k]].tobytes() == m_all[1, t, :c_all[1, t]].tobytes(), (k, t)
+    # threshold monotonicity
+    m_hi, c_hi = ncc.scan_pages(ctx, bank_p, pages[1], 0.9, n_out)
+    bank_p.close()
+    for k in range(T):
+        lo = m_p[0, k, :c_p[0, k]]
+        keep = lo[lo["similarity"] > np.float32(0.9)]
+        if c_p[0, k] < n_out:   # not truncated: exactly the higher-scoring hits
+            assert keep.tobytes() == m_hi[0, k, :c_hi[0, k]].tobytes(), k
+        else:                   # truncated in raster order: they are the first of them
+            assert c_hi[0, k] >= len(keep) and keep.tobytes() == m_hi[0, k, :len(keep)].tobytes(), k
+    assert 0 < c_hi.sum() < c_p.sum()
+
+
 def test_cpp_host_searcher_matches_golden(ctx, golden):
     """The C++ Searcher mirror (host/focr_host.cpp) marshals like ncc.rs:332-404 and reproduces the
     reference's match lists; widths above 16 'panic' like ncc.rs:392."""
