@@ -77,3 +77,33 @@ def test_config4_full_page_and_multi_device(ctx, oracle, font, pkg):
     finally:
         mctx.close()
     assert got_m == got
+
+
+def test_full_size_batch_invariances(ctx, font, pkg, monkeypatch):
+    """focr_decode_pages over 40 full-size pages (three chunks: both slots are reused) from pageable and from pinned host
+    memory, against the same pages decoded one per call; the row-task kernel (FOCR_DECODE_LEGACY) and the band layout
+    (FOCR_DECODE_BAND) must decode the same text as the tile kernel on the compact layout."""
+    import torch
+    from font_ocr_b200 import focr
+
+    alphabet = pkg.raster.FOCR_DEFAULT_ALPHABET
+    distinct = [pkg.pages.make_focr_page(font, 13, 2480, 3508, seed=7300 + i)[0] for i in range(4)]
+    order = [(7 * i + i // 4) % 4 for i in range(40)]
+    pages = np.stack([distinct[k] for k in order])
+    bank = focr.GlyphBank(ctx, font, 13, alphabet)
+    try:
+        single = [focr.decode_images(ctx, bank, d[None], 45, 39, 608, 12, 15)[0] for d in distinct]
+        assert all(len(s) > 200 for s in single)
+        got = focr.decode_images(ctx, bank, pages, 45, 39, 608, 12, 15)                       # pageable: staged gather
+        assert [got[i] == single[k] for i, k in enumerate(order)] == [True] * 40
+        pinned = torch.from_numpy(pages).pin_memory()
+        got_p = focr.decode_images(ctx, bank, pinned.numpy(), 45, 39, 608, 12, 15)             # pinned: strided DMA
+        assert got_p == got
+        monkeypatch.setenv("FOCR_DECODE_LEGACY", "1")
+        assert focr.decode_images(ctx, bank, pages[:5], 45, 39, 608, 12, 15) == got[:5]
+        monkeypatch.delenv("FOCR_DECODE_LEGACY")
+        monkeypatch.setenv("FOCR_DECODE_BAND", "1")
+        assert focr.decode_images(ctx, bank, pinned.numpy()[:5], 45, 39, 608, 12, 15) == got[:5]
+    finally:
+        bank.close()
+
