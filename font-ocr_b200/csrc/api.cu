@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -755,6 +757,71 @@ static int stage_threads()
     return std::max(std::min(base, 4), base / g_stage_sharers.load());
 }
 
+// A small persistent pool for the staging copies: a chunk is staged in 32-MB pieces, and creating and joining a set of
+// threads per piece costs about as much as copying a quarter of it.  run(n, fn) executes fn(0..n-1), fn(0) on the caller.
+// One job at a time per pool; every calling host thread has its own.
+class StagePool {
+    std::mutex job_mu, mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    std::function<void(int)> fn;
+    int n_parts = 0, next = 0, pending = 0;
+    uint64_t epoch = 0;
+    bool stop = false;
+    void loop()
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || (epoch != seen && next < n_parts); });
+            if (stop) return;
+            while (next < n_parts) {
+                const int i = next++;
+                lk.unlock();
+                fn(i);
+                lk.lock();
+                if (--pending == 0) cv_done.notify_all();
+            }
+            seen = epoch;
+        }
+    }
+  public:
+    ~StagePool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void run(int n, const std::function<void(int)> &f)
+    {
+        if (n <= 1) {
+            if (n == 1) f(0);
+            return;
+        }
+        std::lock_guard<std::mutex> job(job_mu);
+        std::unique_lock<std::mutex> lk(mu);
+        while ((int)workers.size() < n - 1) workers.emplace_back([this] { loop(); });
+        fn = f;
+        n_parts = n, next = 1, pending = n - 1;
+        epoch++;
+        lk.unlock();
+        cv_work.notify_all();
+        f(0);
+        lk.lock();
+        cv_done.wait(lk, [&] { return pending == 0; });
+        n_parts = 0;
+    }
+};
+static StagePool &stage_pool()
+{
+    // one pool per calling host thread: the devices of a focr_multi call stage from their own threads at the same time
+    thread_local StagePool p;
+    return p;
+}
+
 // rows x row_bytes from src (stride src_stride) to dst (stride dst_stride), split over the staging threads
 static void parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows)
 {
@@ -765,27 +832,23 @@ static void parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, s
             memcpy(dst, src, total);
             return;
         }
-        std::vector<std::thread> th;
         const size_t per = ((total + nt - 1) / nt + 4095) & ~(size_t)4095;
-        for (int i = 1; i < nt; i++) {
-            const size_t o = std::min(total, per * i), n = std::min(total, per * (i + 1)) - o;
-            if (n) th.emplace_back([=] { memcpy(dst + o, src + o, n); });
-        }
-        memcpy(dst, src, std::min(total, per));
-        for (auto &t : th) t.join();
+        stage_pool().run(nt, [=](int i) {
+            const size_t o = std::min(total, per * (size_t)i), n = std::min(total, per * (size_t)(i + 1)) - o;
+            if (n) memcpy(dst + o, src + o, n);
+        });
         return;
     }
     const int nt = (int)std::max<size_t>(1, std::min<size_t>(stage_threads(), rows));
-    std::vector<std::thread> th;
-    auto work = [=](int i) {
-        for (size_t r = i; r < rows; r += nt) memcpy(dst + r * dst_stride, src + r * src_stride, row_bytes);
-    };
-    for (int i = 1; i < nt; i++) th.emplace_back(work, i);
-    work(0);
-    for (auto &t : th) t.join();
+    stage_pool().run(nt, [=](int i) {
+        for (size_t r = (size_t)i; r < rows; r += (size_t)nt) memcpy(dst + r * dst_stride, src + r * src_stride, row_bytes);
+    });
 }
 
 bool focr_internal_host_pinned(const void *p) { return host_ptr_is_pinned(p); }
+// focr_decode.cu: its row gather runs on the same pool, with the same thread budget
+void focr_internal_parallel_for(int n, const std::function<void(int)> &fn) { stage_pool().run(n, fn); }
+int focr_internal_stage_threads() { return stage_threads(); }
 void focr_internal_parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows)
 {
     parallel_copy(dst, dst_stride, src, src_stride, row_bytes, rows);

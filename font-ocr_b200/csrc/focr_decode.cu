@@ -17,6 +17,7 @@
 // word and the byte-shifted strip word.  Horizontally clipped cells (a line's first / last glyph) take the per-pixel loop.
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -402,6 +403,8 @@ void *focr_internal_stage_begin(focr_ctx *ctx, int stage);
 void focr_internal_stage_end(void *timer);
 void focr_internal_streams(focr_ctx *ctx, cudaStream_t out[3]);   // compute, H2D, D2H
 bool focr_internal_host_pinned(const void *p);
+void focr_internal_parallel_for(int n, const std::function<void(int)> &fn);   // api.cu: the staging thread pool
+int focr_internal_stage_threads();
 void focr_internal_parallel_copy(uint8_t *dst, size_t dst_stride, const uint8_t *src, size_t src_stride, size_t row_bytes, size_t rows);
 
 struct focr_glyph_bank {
@@ -693,11 +696,8 @@ extern "C" int focr_decode_pages(focr_ctx *ctx, const focr_glyph_bank *bank, con
                         }
                     }
                 };
-                const uint32_t nt = std::min<uint32_t>(nB, 4);
-                std::vector<std::thread> th;
-                for (uint32_t t = 1; t < nt; t++) th.emplace_back(gather, t, nt);
-                gather(0, nt);
-                for (auto &t : th) t.join();
+                const uint32_t nt = std::min<uint32_t>(nB, (uint32_t)focr_internal_stage_threads());
+                focr_internal_parallel_for((int)nt, [&](int t) { gather((uint32_t)t, nt); });
             }
             for (uint32_t q = 0; q < nB && !staged; q++) {
                 const uint8_t *sp = src0 + q * page_stride + (size_t)by * r_w + bx;   // first row of line 0 of this page
