@@ -88,6 +88,9 @@ const char *focr_version(void);
 const char *focr_last_error(void); /* thread-local */
 void focr_get_limits(focr_limits *out);
 
+/* A context owns one GPU's streams, scratch and pinned staging.  It is NOT re-entrant: calls that take the same context must
+ * not overlap (one host thread per context at a time -- the reference's rayon workers map to one context per GPU, see
+ * focr_multi below, which runs its contexts from its own host threads).  Different contexts are independent. */
 int focr_ctx_create(int device, focr_ctx **out);
 void focr_ctx_destroy(focr_ctx *ctx);
 int focr_ctx_set_kernel(focr_ctx *ctx, int kernel);
