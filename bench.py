@@ -495,12 +495,43 @@ def config5(ctx, ncc, pkg, font, stream, torch, int8_peak):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs: keep this rank's host threads (and with them its first-touched pinned buffers and the library's
+    staging threads) on the NUMA node its GPU hangs off -- N ranks streaming pages through one host memory system otherwise
+    cross the socket interconnect at random.  Returns what was done, for the bench line.  BENCH_NO_NUMA=1 skips it."""
+    if os.environ.get("BENCH_NO_NUMA"):
+        return {"bound": False, "why": "BENCH_NO_NUMA"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:   # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"bound": False, "why": "the GPU reports no NUMA node"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "no allowed CPU on the GPU's node"}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "node": node, "cpus": len(cpus)}
+    except Exception as e:   # noqa: BLE001 -- a missing sysfs entry must not fail the bench
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     rank, world, local = dist_setup()
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"bound": False, "why": "single rank"}
     cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -766,7 +797,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pages_per_gpu_per_step": P, "distinct_pages": min(args.distinct or P, P),
                        "templates": T, "box_sizes": [[w, h, c] for w, h, c in classes], "kernel": args.kernel,
-                       "l2": "inputs (870 MB per 100 pages) larger than L2; no flush"},
+                       "l2": "inputs (870 MB per 100 pages) larger than L2; no flush", "numa": numa},
             "evals_per_sec": value * evals_page,
             "e2e": {"value": e2e_value, "unit": "pages/s", "h2d_bytes_per_step": int(pages_pin.numel()) * world,
                     "d2h_bytes_per_step": int(out_pin.numel() + counts_pin.numel() * 4) * world,
