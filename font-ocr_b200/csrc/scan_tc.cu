@@ -80,7 +80,6 @@ constexpr int TC_LOOK_GROUPS = 2;     // expanded row groups the producer side m
 constexpr int TC_RING_MAX = 12;       // max ring groups
 constexpr int TC_A2_GROUPS = 4;       // A2 (statistics) ring: up to 4 groups x 4 output rows x 2 KB (2 for tall boxes)
 constexpr int TC_MAX_BUF = 8;         // TMEM accumulator buffers
-constexpr int TC_YSEG = 128;          // output rows per work item (fewer on small batches, see launch_scan_tc)
 // setmaxnreg budget (the kernel is launched with 96 registers x 640 threads = 61440): warps 0-3 (TMA producer, MMA
 // issuers: their state lives in uniform registers) keep 56, Toeplitz warps 40, A2 warps 48, and the 8 epilogue warps, which
 // hold four 32-column units at a time, take 168: 128 x (56 + 40 + 48) + 256 x 168 = 61440
@@ -1461,16 +1460,23 @@ cudaError_t launch_scan_tc(const TcClass &tc, const ScanArgs &a, int n_pages, in
     const int xs = a.r_w - n_w_min + 1, ys = a.r_h - (int)tc.n_h;  // output rows 1 .. r_h-n_h
     if (xs <= 0 || ys <= 0) return cudaSuccess;
     p.n_xstrips = (xs + 127) / 128;
-    // Work items = (page, 128-window strip, y-segment), dealt round-robin to one persistent CTA per SM.  Segments of 128
-    // rows amortise the n_hp-1 extra page rows an item expands; a batch that would leave SMs idle or unbalanced (a single
-    // 608x800 page: 5 strips x 7 segments for 148 SMs) takes as many shorter segments as fill its last wave.
+    // Work items = (page, 128-window strip, y-segment), dealt round-robin to one persistent CTA per SM.  The segment height is
+    // chosen per launch: the kernel takes (rounds of items per CTA) x (rows per item + a per-item cost: the n_hp-1 extra page
+    // rows an item expands and the pipeline refill at its start, ~3 + n_hp/4 rows' worth), so the number of segments that
+    // minimises that product wins -- long segments amortise the per-item cost, but the last round must not be half empty
+    // (16 pages of 2480x3508: 18 segments of 195 rows, 39 full rounds, 1.3 % faster than 28 x 125; a single 608x800 page: 29
+    // segments so that 145 items fill the 148 SMs once).
     {
         const long long cols = (long long)n_pages * p.n_xstrips;
-        const long long segs_min = (ys + TC_YSEG - 1) / TC_YSEG;
-        const long long waves = (cols * segs_min + sm_count - 1) / sm_count;
-        long long segs = segs_min;
-        if (waves < 8) segs = std::max(segs_min, std::min<long long>(waves * sm_count / cols, (ys + 7) / 8));
-        p.yseg = (int)((ys + segs - 1) / segs);
+        const long long item_cost = 3 + p.n_hp / 4;
+        const long long segs_lo = std::max<long long>(1, (ys + 255) / 256), segs_hi = std::max<long long>(segs_lo, (ys + 7) / 8);
+        long long best = -1, best_segs = segs_lo;
+        for (long long segs = segs_lo; segs <= segs_hi; segs++) {
+            const long long rows = (ys + segs - 1) / segs, rounds = (cols * ((ys + rows - 1) / rows) + sm_count - 1) / sm_count;
+            const long long cost = rounds * (rows + item_cost);
+            if (best < 0 || cost < best) best = cost, best_segs = segs;
+        }
+        p.yseg = (int)((ys + best_segs - 1) / best_segs);
     }
     if (const char *e = getenv("FOCR_TC_YSEG")) p.yseg = std::max(1, atoi(e));   // experiments
     p.n_ysegs = (ys + p.yseg - 1) / p.yseg;
