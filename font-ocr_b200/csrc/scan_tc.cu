@@ -919,7 +919,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) scan_tc_kernel(const __grid_con
         const int e = warp - 12;
         const int q = e & 3;                      // TMEM lane quarter this warp may access (warp % 4)
         const int team = e >> 2;                  // which jobs
-        const int m = q * 32 + lane;              // window within the strip
         const uint32_t nbuf = p.nbuf, nsub = p.nsub;
         constexpr int nunits = NUNITS, n2 = nunits - TC_EPI_UNITS;   // n2 > 0: units screened before the release
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
