@@ -814,6 +814,13 @@ class StagePool {
         cv_work.notify_all();
         f(0);
         lk.lock();
+        while (next < n_parts) {   // workers that are slow to wake (an oversubscribed host) do not hold the job up
+            const int i = next++;
+            lk.unlock();
+            f(i);
+            lk.lock();
+            --pending;
+        }
         cv_done.wait(lk, [&] { return pending == 0; });
         n_parts = 0;
     }

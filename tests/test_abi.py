@@ -1,5 +1,6 @@
 """The drop-in boundary: the library builds for sm_100a, loads without a GPU, exports every symbol
 include/focr_b200.h declares, and refuses to compute without a device (no CPU fallback)."""
+import numpy as np
 import ctypes as C
 import os
 import re
@@ -64,3 +65,46 @@ def test_product_never_imports_oracle():
                 s = open(os.path.join(dp, f)).read()
                 assert "from oracle" not in s and "import oracle" not in s and "libncc_oracle" not in s \
                     and "libncc_ref" not in s, os.path.join(dp, f)
+
+
+def test_staging_pool_copies(built_lib):
+    """The staging copies (pageable callers: api.cu `parallel_copy` on its persistent per-thread pool) need no GPU: contiguous
+    and strided copies of many sizes, repeated (the pool is reused), and from several host threads at once (one pool each,
+    like the devices of a focr_multi call) must move every byte."""
+    import ctypes as C
+    import threading
+
+    lib = C.CDLL(built_lib)
+    copy = getattr(lib, "_Z27focr_internal_parallel_copyPhmPKhmmm")   # (dst, dst_stride, src, src_stride, row_bytes, rows), C++ linkage
+    copy.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+    copy.restype = None
+    rng = np.random.default_rng(3)
+
+    def work(seed, errors):
+        r = np.random.default_rng(seed)
+        for it in range(12):
+            n = int(r.integers(1, 24 << 20))
+            src = r.integers(0, 256, n, dtype=np.uint8)
+            dst = np.zeros(n, np.uint8)
+            copy(dst.ctypes.data, 0, src.ctypes.data, 0, n, 1)                       # one contiguous block
+            if not np.array_equal(src, dst):
+                errors.append(("contiguous", seed, it))
+            rows, rb = int(r.integers(1, 3000)), int(r.integers(1, 5000))
+            ss, ds = rb + int(r.integers(0, 64)), rb + int(r.integers(0, 64))
+            src2 = r.integers(0, 256, rows * ss, dtype=np.uint8)
+            dst2 = np.full(rows * ds, 7, np.uint8)
+            copy(dst2.ctypes.data, ds, src2.ctypes.data, ss, rb, rows)               # strided rows
+            a = src2.reshape(rows, ss)[:, :rb]
+            b = dst2.reshape(rows, ds)
+            if not (np.array_equal(a, b[:, :rb]) and (b[:, rb:] == 7).all()):
+                errors.append(("strided", seed, it))
+
+    errors = []
+    work(int(rng.integers(1 << 30)), errors)
+    threads = [threading.Thread(target=work, args=(100 + i, errors)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
